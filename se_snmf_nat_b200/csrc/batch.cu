@@ -1,0 +1,357 @@
+// Whole-batch entry: the hop loops of filewise_run_IS16.m:86-169 for n_utt utterances advanced in lock step on
+// one GPU.  STFT of every frame up front (batched cuFFT), then one {H-solve, gain, W-solve} kernel triple per
+// hop over all still-active utterances, then ISTFT + overlap-add of every frame.
+#include <algorithm>
+#include <memory>
+#include <cstring>
+#include <numeric>
+#include "state.cuh"
+
+using namespace snmfnat;
+
+struct snmfnat_batch {
+  snmfnat_ctx* ctx = nullptr;
+  Config cfg;
+  int n_utt = 0;
+  std::vector<int64_t> len, out_len, out_off_h, pcm_off_h;
+  std::vector<int> n_hops_u;       // per utterance
+  std::vector<int> order;          // slot -> utterance (sorted by hops, longest first)
+  std::vector<int> slot_of;        // utterance -> slot
+  std::vector<long long> frame_base_u;
+  std::vector<int> active_at;      // active_at[g] = number of active slots at global step g
+  int max_hops = 0;
+  long long NF = 0;                // total frames
+  int64_t pcm_total = 0, out_total = 0;
+  SlotBuffers sb;
+  DevBuf<int16_t> pcm, out;
+  DevBuf<long long> d_pcm_off, d_len, d_frame_base_u, d_out_off;
+  DevBuf<int> d_n_hops_u;
+  DevBuf<double> frames, Ym, Xt;
+  DevBuf<double2> Yc;
+  DevBuf<double> trA, trQ, trG;
+  DevBuf<int> trInfo;
+  bool trace = false, uploaded = false, ran = false;
+  FftPlans fft;
+  int64_t launches_last = 0;
+};
+
+static UttTables utt_tables(const snmfnat_batch* b) {
+  UttTables t{};
+  t.pcm_off = b->d_pcm_off.p; t.len = b->d_len.p; t.frame_base = b->d_frame_base_u.p; t.n_hops = b->d_n_hops_u.p;
+  t.out_off = b->d_out_off.p; t.n_utt = b->n_utt; t.max_hops = b->max_hops;
+  return t;
+}
+
+extern "C" {
+
+int snmfnat_batch_create(snmfnat_ctx* ctx, const snmfnat_params* p, const double* win_stft, const double* win_istft,
+                         const double* B_x, const double* B_d, int n2, int n_utt, const int64_t* len,
+                         const int32_t* chain_id, const double* h_init, const double* Ad_blk_init, int64_t ad_stride,
+                         snmfnat_batch** out) {
+  SN_API_BEGIN
+  SN_REQUIRE(ctx && p && win_stft && win_istft && B_x && B_d && len && h_init && out, SNMFNAT_EINVAL, "NULL argument");
+  SN_REQUIRE(n_utt > 0, SNMFNAT_EINVAL, "n_utt must be positive");
+  SN_REQUIRE(chain_id == nullptr, SNMFNAT_EUNSUPPORTED, "chain mode (B_D_u.mat carry-over) is not implemented yet");
+  SN_REQUIRE(p->adapt_train_N == 0 || p->R_a == 0 || Ad_blk_init != nullptr, SNMFNAT_EINVAL,
+             "Ad_blk_init is required when adaptation is on (init_buff.m:38 draws it with rand)");
+  SN_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<snmfnat_batch> b(new snmfnat_batch());
+  b->ctx = ctx;
+  make_config(ctx, *p, n2, b->cfg);
+  const Config& c = b->cfg;
+  SN_REQUIRE(hsolve_smem_bytes(c.d) <= (size_t)ctx->max_smem_optin, SNMFNAT_EUNSUPPORTED,
+             "basis [B_x B_d] (%d x %d) does not fit the 4-CTA shared-memory H-solve", c.d.F, c.d.R);
+  b->n_utt = n_utt;
+  b->len.assign(len, len + n_utt);
+  b->n_hops_u.resize(n_utt); b->out_len.resize(n_utt); b->pcm_off_h.resize(n_utt); b->out_off_h.resize(n_utt);
+  b->frame_base_u.resize(n_utt);
+  int64_t po = 0, oo = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    SN_REQUIRE(len[u] >= 0 && len[u] / c.g.shift < (1 << 30), SNMFNAT_EINVAL, "bad length of utterance %d", u);
+    const int nh = (int)(len[u] / c.g.shift) + c.g.delay + 1;  // filewise_run_IS16.m:102-123
+    b->n_hops_u[u] = nh;
+    b->out_len[u] = (int64_t)(nh - c.g.delay) * c.g.shift;     // :146,165
+    b->pcm_off_h[u] = po;
+    po += (len[u] + 7) / 8 * 8;
+    b->out_off_h[u] = oo;
+    oo += (b->out_len[u] + 7) / 8 * 8;
+  }
+  b->pcm_total = po; b->out_total = oo;
+  // slots: one per utterance, longest first, so the active set at any step is a prefix
+  b->order.resize(n_utt);
+  std::iota(b->order.begin(), b->order.end(), 0);
+  std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int q) { return b->n_hops_u[a] > b->n_hops_u[q]; });
+  b->slot_of.resize(n_utt);
+  long long fb = 0;
+  std::vector<long long> fb_slot(n_utt);
+  std::vector<int> nh_slot(n_utt), loff(n_utt, 0);
+  for (int s = 0; s < n_utt; ++s) {
+    const int u = b->order[s];
+    b->slot_of[u] = s;
+    fb_slot[s] = fb;
+    b->frame_base_u[u] = fb;
+    nh_slot[s] = b->n_hops_u[u];
+    fb += b->n_hops_u[u];
+  }
+  b->NF = fb;
+  b->max_hops = nh_slot[0];
+  b->active_at.assign(b->max_hops, 0);
+  for (int g = 0, s = n_utt; g < b->max_hops; ++g) {
+    while (s > 0 && nh_slot[s - 1] <= g) --s;
+    b->active_at[g] = s;
+  }
+  // device buffers
+  b->sb.alloc(n_utt, c.d);
+  b->sb.set_bases(ctx, B_x, B_d);
+  if (c.sc.adapt_train_N) b->sb.set_ad_init(ctx, Ad_blk_init, ad_stride, b->order);
+  b->sb.win_stft.alloc(c.g.sz); b->sb.win_istft.alloc(c.g.sz);
+  SN_CUDA(cudaMemcpy(b->sb.win_stft.p, win_stft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
+  SN_CUDA(cudaMemcpy(b->sb.win_istft.p, win_istft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
+  SN_CUDA(cudaMemcpy(b->sb.h_init.p, h_init, c.d.R * sizeof(double), cudaMemcpyHostToDevice));
+  SN_CUDA(cudaMemcpy(b->sb.l_offset.p, loff.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice));
+  SN_CUDA(cudaMemcpy(b->sb.n_hops.p, nh_slot.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice));
+  SN_CUDA(cudaMemcpy(b->sb.frame_base.p, fb_slot.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice));
+  b->pcm.alloc((size_t)std::max<int64_t>(po, 8));
+  b->out.alloc((size_t)std::max<int64_t>(oo, 8));
+  b->d_pcm_off.alloc(n_utt); b->d_len.alloc(n_utt); b->d_frame_base_u.alloc(n_utt); b->d_out_off.alloc(n_utt);
+  b->d_n_hops_u.alloc(n_utt);
+  {
+    std::vector<long long> t(n_utt);
+    for (int u = 0; u < n_utt; ++u) t[u] = b->pcm_off_h[u];
+    SN_CUDA(cudaMemcpy(b->d_pcm_off.p, t.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice));
+    for (int u = 0; u < n_utt; ++u) t[u] = b->len[u];
+    SN_CUDA(cudaMemcpy(b->d_len.p, t.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice));
+    for (int u = 0; u < n_utt; ++u) t[u] = b->out_off_h[u];
+    SN_CUDA(cudaMemcpy(b->d_out_off.p, t.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice));
+    SN_CUDA(cudaMemcpy(b->d_frame_base_u.p, b->frame_base_u.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice));
+    SN_CUDA(cudaMemcpy(b->d_n_hops_u.p, b->n_hops_u.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  b->frames.alloc((size_t)b->NF * c.g.fftlen);
+  b->Yc.alloc((size_t)b->NF * c.g.half);
+  b->Ym.alloc((size_t)b->NF * c.d.LDF);
+  b->Xt.alloc((size_t)b->NF * c.d.LDF);
+  b->fft.create(ctx, c.g.fftlen, b->NF);
+  SN_CUDA(cudaMemset(b->pcm.p, 0, b->pcm.n * sizeof(int16_t)));
+  *out = b.release();
+  SN_API_END
+}
+
+int snmfnat_batch_destroy(snmfnat_batch* b) {
+  SN_API_BEGIN
+  if (b) {
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    delete b;
+  }
+  SN_API_END
+}
+
+int snmfnat_batch_upload(snmfnat_batch* b, const int16_t* const* pcm) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && pcm, SNMFNAT_EINVAL, "NULL argument");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  for (int u = 0; u < b->n_utt; ++u)
+    if (b->len[u] > 0)
+      SN_CUDA(cudaMemcpyAsync(b->pcm.p + b->pcm_off_h[u], pcm[u], b->len[u] * sizeof(int16_t), cudaMemcpyHostToDevice,
+                              b->ctx->stream));
+  SN_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  b->uploaded = true;
+  SN_API_END
+}
+
+int snmfnat_batch_upload_packed(snmfnat_batch* b, const int16_t* pcm_packed) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && pcm_packed, SNMFNAT_EINVAL, "NULL argument");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  int64_t off = 0;
+  for (int u = 0; u < b->n_utt; ++u) {
+    if (b->len[u] > 0)
+      SN_CUDA(cudaMemcpyAsync(b->pcm.p + b->pcm_off_h[u], pcm_packed + off, b->len[u] * sizeof(int16_t),
+                              cudaMemcpyHostToDevice, b->ctx->stream));
+    off += b->len[u];
+  }
+  b->uploaded = true;
+  SN_API_END
+}
+
+int snmfnat_batch_enable_trace(snmfnat_batch* b, int on) {
+  SN_API_BEGIN
+  SN_REQUIRE(b, SNMFNAT_EINVAL, "NULL argument");
+  if (on && !b->trace) {
+    b->trA.alloc((size_t)b->NF * b->cfg.d.R);
+    b->trQ.alloc((size_t)b->NF * b->cfg.d.LDF);
+    b->trG.alloc((size_t)b->NF * b->cfg.d.LDF);
+    b->trInfo.alloc((size_t)b->NF * 4);
+  }
+  b->trace = on != 0;
+  SN_API_END
+}
+
+int snmfnat_batch_run(snmfnat_batch* b) {
+  SN_API_BEGIN
+  SN_REQUIRE(b, SNMFNAT_EINVAL, "NULL argument");
+  SN_REQUIRE(b->uploaded, SNMFNAT_EINVAL, "snmfnat_batch_upload must be called before snmfnat_batch_run");
+  snmfnat_ctx* ctx = b->ctx;
+  SN_CUDA(cudaSetDevice(ctx->device));
+  const Config& c = b->cfg;
+  const int64_t l0 = ctx->launches;
+  b->sb.reset(ctx);
+  const UttTables ut = utt_tables(b);
+  // STFT of every frame
+  launch_frame_pcm(ctx, c.g, ut, b->pcm.p, b->sb.win_stft.p, b->frames.p);
+  SN_CUFFT(cufftExecD2Z(b->fft.fwd, b->frames.p, reinterpret_cast<cufftDoubleComplex*>(b->Yc.p)));
+  launch_stft_post(ctx, c.g, b->Yc.p, b->NF, b->Ym.p, nullptr);
+  // hop loop
+  const SlotState st = b->sb.view();
+  FrameArrays fr{b->Ym.p, b->Xt.p};
+  TraceArrays tr{b->trA.p, b->trQ.p, b->trG.p, b->trInfo.p};
+  const TraceArrays* trp = b->trace ? &tr : nullptr;
+  for (int g = 0; g < b->max_hops; ++g) {
+    const int na = b->active_at[g];
+    launch_hsolve(ctx, c.d, c.sc, st, fr, b->sb.h_init.p, na, g);
+    launch_gain(ctx, c.d, c.sc, st, fr, trp, na, g);
+    launch_wsolve(ctx, c.d, c.sc, st, trp, na, g);
+  }
+  // ISTFT + overlap-add
+  launch_istft_pre(ctx, c.g, b->Yc.p, b->Xt.p, b->NF);
+  SN_CUFFT(cufftExecZ2D(b->fft.inv, reinterpret_cast<cufftDoubleComplex*>(b->Yc.p), b->frames.p));
+  int windowed = 0;
+  if (c.g.preemph != 0.0) {
+    launch_synth_window(ctx, c.g, b->frames.p, b->sb.win_istft.p, b->NF);
+    windowed = 1;
+  }
+  launch_ola_int16(ctx, c.g, ut, b->frames.p, b->sb.win_istft.p, windowed, b->out.p);
+  b->launches_last = ctx->launches - l0;
+  b->ran = true;
+  SN_API_END
+}
+
+static void check_err_flag(snmfnat_batch* b) {
+  int flag = 0;
+  SN_CUDA(cudaMemcpyAsync(&flag, b->sb.err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, b->ctx->stream));
+  SN_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  SN_REQUIRE(flag == 0, SNMFNAT_ENUMERIC,
+             "an all-zero activation row was selected for adaptation (reference dimension mismatch, "
+             "bnmf_sep_event_RT_IS16.m:292 vs :323)");
+}
+
+int snmfnat_batch_download(snmfnat_batch* b, int16_t* const* out) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && out, SNMFNAT_EINVAL, "NULL argument");
+  SN_REQUIRE(b->ran, SNMFNAT_EINVAL, "snmfnat_batch_run has not been called");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  for (int u = 0; u < b->n_utt; ++u)
+    SN_CUDA(cudaMemcpyAsync(out[u], b->out.p + b->out_off_h[u], b->out_len[u] * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                            b->ctx->stream));
+  check_err_flag(b);
+  SN_API_END
+}
+
+int snmfnat_batch_download_packed(snmfnat_batch* b, int16_t* out_packed) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && out_packed, SNMFNAT_EINVAL, "NULL argument");
+  SN_REQUIRE(b->ran, SNMFNAT_EINVAL, "snmfnat_batch_run has not been called");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  int64_t off = 0;
+  for (int u = 0; u < b->n_utt; ++u) {
+    SN_CUDA(cudaMemcpyAsync(out_packed + off, b->out.p + b->out_off_h[u], b->out_len[u] * sizeof(int16_t),
+                            cudaMemcpyDeviceToHost, b->ctx->stream));
+    off += b->out_len[u];
+  }
+  check_err_flag(b);
+  SN_API_END
+}
+
+int64_t snmfnat_batch_out_len(const snmfnat_batch* b, int u) {
+  if (!b || u < 0 || u >= b->n_utt) return -1;
+  return b->out_len[u];
+}
+int64_t snmfnat_batch_total_hops(const snmfnat_batch* b) { return b ? b->NF : -1; }
+
+int snmfnat_batch_get_stats(snmfnat_batch* b, snmfnat_batch_stats* out) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && out, SNMFNAT_EINVAL, "NULL argument");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  unsigned long long s[8];
+  SN_CUDA(cudaMemcpyAsync(s, b->sb.stats.p, sizeof(s), cudaMemcpyDeviceToHost, b->ctx->stream));
+  SN_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  std::memset(out, 0, sizeof(*out));
+  out->hops = (int64_t)s[0]; out->h_iters = (int64_t)s[1]; out->w_iters = (int64_t)s[2]; out->gated_hops = (int64_t)s[3];
+  out->w_solves = (int64_t)s[4]; out->w_atoms = (int64_t)s[5];
+  // flops = sum_hops [ it_h*(4FR+10F) + it_w*(4*F*R_up*m_a + 12*F*m_a) + 0.7e6 ]; the W-solve term uses
+  // the mean R_up of the run (sum over solves of it_w*R_up is approximated by w_iters * mean R_up).
+  const Config& c = b->cfg;
+  const double F = c.d.F, R = c.d.R, ma = c.d.m_a;
+  const double mean_rup = s[4] ? (double)s[5] / (double)s[4] : 0.0;
+  out->flops = (double)s[1] * (4.0 * F * R + 10.0 * F) + (double)s[2] * (4.0 * F * mean_rup * ma + 12.0 * F * ma) +
+               (double)s[0] * 0.7e6;
+  out->launches = b->launches_last;
+  SN_API_END
+}
+
+int snmfnat_batch_get_trace(snmfnat_batch* b, int u, const char* what, double* buf, int64_t n) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && what && buf, SNMFNAT_EINVAL, "NULL argument");
+  SN_REQUIRE(u >= 0 && u < b->n_utt, SNMFNAT_EINVAL, "utterance index out of range");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  SN_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  const Config& c = b->cfg;
+  const long long f0 = b->frame_base_u[u];
+  const int nh = b->n_hops_u[u];
+  const std::string w(what);
+  auto rows = [&](const double* src, int ld, int width) {
+    SN_REQUIRE(n >= (int64_t)nh * width, SNMFNAT_EINVAL, "buffer too small: need %lld doubles", (long long)nh * width);
+    SN_CUDA(cudaMemcpy2D(buf, (size_t)width * sizeof(double), src + (size_t)f0 * ld, (size_t)ld * sizeof(double),
+                         (size_t)width * sizeof(double), nh, cudaMemcpyDeviceToHost));
+  };
+  if (w == "Xm_tilde") { rows(b->Xt.p, c.d.LDF, c.d.F); }
+  else if (w == "Ym") { rows(b->Ym.p, c.d.LDF, c.d.F); }
+  else {
+    SN_REQUIRE(b->trace && b->trA.p, SNMFNAT_EINVAL, "tracing was not enabled before the run");
+    if (w == "A") rows(b->trA.p, c.d.R, c.d.R);
+    else if (w == "Q") rows(b->trQ.p, c.d.LDF, c.d.F);
+    else if (w == "G") rows(b->trG.p, c.d.LDF, c.d.F);
+    else {
+      int col = -1;
+      if (w == "h_iters") col = 0; else if (w == "gated") col = 1; else if (w == "R_a_up") col = 2; else if (w == "w_iters") col = 3;
+      SN_REQUIRE(col >= 0, SNMFNAT_EINVAL, "unknown trace field '%s'", what);
+      SN_REQUIRE(n >= nh, SNMFNAT_EINVAL, "buffer too small");
+      std::vector<int> tmp((size_t)nh * 4);
+      SN_CUDA(cudaMemcpy(tmp.data(), b->trInfo.p + (size_t)f0 * 4, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < nh; ++i) buf[i] = tmp[(size_t)i * 4 + col];
+    }
+  }
+  SN_API_END
+}
+
+int snmfnat_batch_get_noise_basis(snmfnat_batch* b, int u, double* B_d) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && B_d, SNMFNAT_EINVAL, "NULL argument");
+  SN_REQUIRE(u >= 0 && u < b->n_utt, SNMFNAT_EINVAL, "utterance index out of range");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  SN_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  const Config& c = b->cfg;
+  const int s = b->slot_of[u];
+  int sel = 0;
+  SN_CUDA(cudaMemcpy(&sel, b->sb.bd_sel.p + s, sizeof(int), cudaMemcpyDeviceToHost));
+  const double* src = (sel ? b->sb.Bd1.p : b->sb.Bd0.p) + (size_t)s * c.d.R_d * c.d.LDF;
+  download_basis(b->ctx, src, c.d.F, c.d.R_d, c.d.LDF, B_d);
+  SN_API_END
+}
+
+int snmfnat_enhance_batch(snmfnat_ctx* ctx, const snmfnat_params* p, const double* win_stft, const double* win_istft,
+                          const double* B_x, const double* B_d, int n2, int n_utt, const int16_t* const* pcm,
+                          const int64_t* len, const int32_t* chain_id, const double* h_init, const double* Ad_blk_init,
+                          int64_t ad_stride, int16_t* const* out) {
+  snmfnat_batch* b = nullptr;
+  int rc = snmfnat_batch_create(ctx, p, win_stft, win_istft, B_x, B_d, n2, n_utt, len, chain_id, h_init, Ad_blk_init,
+                                ad_stride, &b);
+  if (rc) return rc;
+  rc = snmfnat_batch_upload(b, pcm);
+  if (!rc) rc = snmfnat_batch_run(b);
+  if (!rc) rc = snmfnat_batch_download(b, out);
+  snmfnat_batch_destroy(b);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Device-resident state of a set of audio streams ("slots") and the launchers of the per-hop kernels.
+// One slot = the struct g of src/init_buff.m:17-62 for one stream, laid out for the kernels:
+//   - every F-long vector / basis column has padded leading dimension LDF (multiple of 8 doubles)
+//   - history matrices (lambda_d_blk, Ad_blk, r_blk) are ring buffers indexed by time slot
+//   - the adapted noise basis is double-buffered (the reference re-orders its columns on every update,
+//     bnmf_sep_event_RT_IS16.m:336)
+#pragma once
+#include "common.cuh"
+
+namespace snmfnat {
+
+struct OnlineDims {
+  int F;      // n2 = fftlength/2+1 rows of the DFT-domain vectors
+  int LDF;    // padded F
+  int R_x, R_d, R, R_a, m_a, P_len_l;
+};
+
+// Scalars of p used inside the kernels.
+struct OnlineScalars {
+  double flr;            // p.nonzerofloor (also sparse_nmf's flr = 1e-9, sparse_nmf.m:166)
+  double sparsity, conv_eps;
+  int max_iter, cost_check;
+  int DCbin, init_N_len, adapt_train_N, blk_sparse, P_len_k, P_len_l, blk_gap;
+  double alpha_p, alpha_eta, alpha_d, beta, beta_max, Ar_up;
+  int enhance_method;
+  int update_period;     // floor(p.overlap_m_a * p.m_a), bnmf_sep_event_RT_IS16.m:293
+};
+
+// Pointers into the per-slot state arrays (slot-major).
+struct SlotState {
+  int S;                        // number of slots
+  const double* Bx;             // [R_x][LDF] speech basis, shared by all slots (never changes in DFT mode)
+  const double* Bd_fix;         // [R_d][LDF] the "B_Mel_d" slot in DFT mode: initial noise basis per slot? shared
+  size_t bdfix_stride;          // 0 when shared by all slots, R_d*LDF when per slot (chains)
+  double* Bd[2];                // [S][R_d][LDF] ping-pong adapted noise basis
+  int* bd_sel;                  // [S] current buffer
+  double* Ad_blk;               // [S][m_a][R_a]   ring (time-slot major)
+  double* lam_blk;              // [S][m_a][LDF]   ring
+  int* ring_head;               // [S] oldest time slot == next to overwrite
+  double* r_blk;                // [S][P_len_l][LDF] ring, slot (l-1) % P_len_l
+  double* lambda_dav;           // [S][LDF]
+  double* Xm_tilde_prev;        // [S][LDF]
+  int* update_switch;           // [S]
+  // per-hop scratch
+  double* A;                    // [S][R]   activations of the H-solve (the reference's A)
+  double* Xhat;                 // [S][LDF] B_x*A_x   (sum over event classes)
+  double* Dhat;                 // [S][LDF] B_d*A_d
+  double* Q;                    // [S][LDF]
+  double* G;                    // [S][LDF]
+  int* h_iters;                 // [S]
+  double* h_cost;               // [S]
+  int* gated;                   // [S]
+  int* do_update;               // [S] W-solve requested this hop
+  int* n_up;                    // [S]
+  int* idx_up;                  // [S][R_a]
+  int* idx_rem;                 // [S][R_a]
+  int* w_iters;                 // [S]
+  int* err_flag;                // [1] set when the reference would hit a dimension mismatch
+  // hop bookkeeping
+  const int* l_offset;          // [S] local hop index l = g_step + 1 - l_offset[s]  (1-based)
+  const int* n_hops;            // [S] hops of the current utterance of this slot (slot inactive when l > n_hops)
+  const long long* frame_base;  // [S] frame index of (slot, g_step = 0)
+  // accumulators
+  unsigned long long* stats;    // [8]: hops, h_iters, w_iters, gated, w_solves, w_atoms
+};
+
+// Per-frame arrays shared by the STFT, the solvers and the ISTFT.
+struct FrameArrays {
+  const double* Ym;   // [NF][LDF]  |Y|^pow (+floor, DC zeroed)
+  double* Xt;         // [NF][LDF]  enhanced spectrum G.*Ym
+};
+
+// Optional per-hop trace for parity tests ([NF] rows).
+struct TraceArrays {
+  double* A;       // [NF][R]
+  double* Q;       // [NF][LDF]
+  double* G;       // [NF][LDF]
+  int* info;       // [NF][4]  h_iters, gated, n_up, w_iters
+};
+
+// ---- launchers (online_kernels.cu) ----
+// H-solve + reconstruction for slots [0, n_active) at global step g_step.
+void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                   const FrameArrays& fr, const double* h_init, int n_active, int g_step);
+// blk_sparse + gain + adaptation gate/history for slots [0, n_active).
+void launch_gain(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                 const FrameArrays& fr, const TraceArrays* tr, int n_active, int g_step);
+// W-solve (noise-basis adaptation) for the slots whose do_update flag is set.
+void launch_wsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                   const TraceArrays* tr, int n_active, int g_step);
+// shared-memory footprints (bytes) so that callers can reject configurations that do not fit
+size_t hsolve_smem_bytes(const OnlineDims& d);
+size_t wsolve_smem_bytes(const OnlineDims& d);
+
+}  // namespace snmfnat

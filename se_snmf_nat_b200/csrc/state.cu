@@ -1,0 +1,148 @@
+#include <cmath>
+#include <cstring>
+#include "state.cuh"
+
+namespace snmfnat {
+
+void make_config(snmfnat_ctx* ctx, const snmfnat_params& p, int n2, Config& cfg) {
+  (void)ctx;
+  // Configurations the reference's IS16 frame function cannot run itself (index errors):
+  SN_REQUIRE(p.blk_len_sep == 1 && p.blk_hop_sep == 1 && p.Splice == 0, SNMFNAT_EUNSUPPORTED,
+             "blk_len_sep>1 / Splice>0 are not runnable in bnmf_sep_event_RT_IS16 (Ym is local, :86-100)");
+  SN_REQUIRE(p.fftlength >= p.framelength && p.fftlength % 2 == 0 && p.framelength > 0 && p.frameshift > 0,
+             SNMFNAT_EINVAL, "bad frame geometry");
+  SN_REQUIRE(n2 == p.fftlength / 2 + 1, SNMFNAT_EINVAL, "basis has %d rows, expected fftlength/2+1 = %d", n2,
+             p.fftlength / 2 + 1);
+  SN_REQUIRE(p.B_sep_mode == SNMFNAT_SEP_DFT, SNMFNAT_EUNSUPPORTED, "B_sep_mode='Mel' is not implemented yet");
+  SN_REQUIRE(p.cf == SNMFNAT_CF_KL, SNMFNAT_EUNSUPPORTED, "online path implements cf='kl' only");
+  SN_REQUIRE(p.basis_update_N == 0 && p.basis_update_E == 0, SNMFNAT_EUNSUPPORTED,
+             "basis_update_N/E (W-update inside the separation solve) is not implemented");
+  SN_REQUIRE(p.R_x > 0 && p.R_d > 0 && p.R_a >= 0 && p.R_a <= p.R_d, SNMFNAT_EINVAL, "bad ranks");
+  SN_REQUIRE(p.m_a > 0 && p.P_len_l > 0 && p.max_iter >= 0, SNMFNAT_EINVAL, "bad m_a / P_len_l / max_iter");
+  SN_REQUIRE(p.DCbin >= 0 && p.DCbin < n2 && p.DCbin_back >= 0 && p.DCbin_back <= n2, SNMFNAT_EINVAL, "bad DCbin");
+  SN_REQUIRE(p.EVENT_NUM >= 1 && p.EVENT_NUM <= SNMFNAT_MAX_CLASSES && p.NOISE_NUM >= 1 &&
+                 p.NOISE_NUM <= SNMFNAT_MAX_CLASSES, SNMFNAT_EINVAL, "bad class counts");
+  SN_REQUIRE(p.pow > 0, SNMFNAT_EINVAL, "pow must be positive");
+  cfg.p = p;
+  OnlineDims& d = cfg.d;
+  d.F = n2;
+  d.LDF = pad_ld(n2);
+  d.R_x = p.R_x; d.R_d = p.R_d; d.R = p.R_x + p.R_d; d.R_a = p.R_a; d.m_a = p.m_a; d.P_len_l = p.P_len_l;
+  OnlineScalars& s = cfg.sc;
+  s.flr = p.nonzerofloor;
+  s.sparsity = p.sparsity; s.conv_eps = p.conv_eps; s.max_iter = p.max_iter; s.cost_check = p.cost_check;
+  s.DCbin = p.DCbin; s.init_N_len = p.init_N_len; s.adapt_train_N = p.adapt_train_N && p.R_a > 0;
+  s.blk_sparse = p.blk_sparse; s.P_len_k = p.P_len_k; s.P_len_l = p.P_len_l; s.blk_gap = p.blk_gap;
+  s.alpha_p = p.alpha_p; s.alpha_eta = p.alpha_eta; s.alpha_d = p.alpha_d; s.beta = p.beta; s.beta_max = p.beta_max;
+  s.Ar_up = p.Ar_up; s.enhance_method = p.ENHANCE_METHOD;
+  s.update_period = (int)std::floor(p.overlap_m_a * (double)p.m_a);  // bnmf_sep_event_RT_IS16.m:293
+  StftGeom& g = cfg.g;
+  g.sz = p.framelength; g.shift = p.frameshift; g.fftlen = p.fftlength; g.half = n2; g.LDF = d.LDF; g.delay = p.delay;
+  g.preemph = p.preemph; g.pow_ = p.pow; g.flr = p.nonzerofloor; g.overlapscale = p.overlapscale;
+  g.DCbin = p.DCbin; g.DCbin_back = p.DCbin_back;
+}
+
+void upload_basis(snmfnat_ctx* ctx, const double* host, int F, int R, int LDF, double* dev) {
+  SN_CUDA(cudaMemsetAsync(dev, 0, (size_t)R * LDF * sizeof(double), ctx->stream));
+  SN_CUDA(cudaMemcpy2DAsync(dev, (size_t)LDF * sizeof(double), host, (size_t)F * sizeof(double),
+                            (size_t)F * sizeof(double), R, cudaMemcpyHostToDevice, ctx->stream));
+  SN_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+void download_basis(snmfnat_ctx* ctx, const double* dev, int F, int R, int LDF, double* host) {
+  SN_CUDA(cudaMemcpy2DAsync(host, (size_t)F * sizeof(double), dev, (size_t)LDF * sizeof(double),
+                            (size_t)F * sizeof(double), R, cudaMemcpyDeviceToHost, ctx->stream));
+  SN_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void SlotBuffers::alloc(int S_, const OnlineDims& d_) {
+  S = S_;
+  d = d_;
+  const size_t LDF = d.LDF;
+  Bx.alloc((size_t)d.R_x * LDF);
+  Bd_fix.alloc((size_t)d.R_d * LDF);
+  Bd0.alloc((size_t)S * d.R_d * LDF);
+  Bd1.alloc((size_t)S * d.R_d * LDF);
+  Ad_blk.alloc((size_t)S * d.m_a * d.R_a);
+  Ad_init.alloc((size_t)S * d.m_a * d.R_a);
+  lam_blk.alloc((size_t)S * d.m_a * LDF);
+  r_blk.alloc((size_t)S * d.P_len_l * LDF);
+  lambda_dav.alloc((size_t)S * LDF);
+  Xm_tilde_prev.alloc((size_t)S * LDF);
+  A.alloc((size_t)S * d.R);
+  Xhat.alloc((size_t)S * LDF);
+  Dhat.alloc((size_t)S * LDF);
+  Q.alloc((size_t)S * LDF);
+  G.alloc((size_t)S * LDF);
+  h_cost.alloc(S);
+  h_init.alloc(d.R);
+  bd_sel.alloc(S); ring_head.alloc(S); update_switch.alloc(S); h_iters.alloc(S); gated.alloc(S);
+  do_update.alloc(S); n_up.alloc(S); w_iters.alloc(S); err_flag.alloc(1);
+  idx_up.alloc((size_t)S * (d.R_a > 0 ? d.R_a : 1));
+  idx_rem.alloc((size_t)S * (d.R_a > 0 ? d.R_a : 1));
+  l_offset.alloc(S); n_hops.alloc(S); frame_base.alloc(S);
+  stats.alloc(8);
+}
+
+void SlotBuffers::set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B_d) {
+  upload_basis(ctx, B_x, d.F, d.R_x, d.LDF, Bx.p);
+  upload_basis(ctx, B_d, d.F, d.R_d, d.LDF, Bd_fix.p);
+}
+
+void SlotBuffers::set_ad_init(snmfnat_ctx* ctx, const double* Ad_blk_init, int64_t stride,
+                              const std::vector<int>& order) {
+  // MATLAB R_a x m_a column-major == [m_a][R_a] time-slot major: the ring layout, oldest column first
+  const size_t per = (size_t)d.m_a * d.R_a;
+  if (per == 0) return;
+  for (int s = 0; s < S; ++s) {
+    const double* src = Ad_blk_init + (stride ? (size_t)order[s] * stride : 0);
+    SN_CUDA(cudaMemcpyAsync(Ad_init.p + (size_t)s * per, src, per * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SN_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void broadcast_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t per, int S) {
+  const size_t total = per * (size_t)S;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i % per];
+}
+
+void SlotBuffers::reset(snmfnat_ctx* ctx) {
+  cudaStream_t st = ctx->stream;
+  lam_blk.zero(st); r_blk.zero(st); lambda_dav.zero(st); Xm_tilde_prev.zero(st);
+  A.zero(st); Xhat.zero(st); Dhat.zero(st); Q.zero(st); G.zero(st); h_cost.zero(st);
+  bd_sel.zero(st); ring_head.zero(st); h_iters.zero(st); gated.zero(st); do_update.zero(st); n_up.zero(st);
+  w_iters.zero(st); err_flag.zero(st); idx_up.zero(st); idx_rem.zero(st); stats.zero(st);
+  fill_int_kernel<<<(S + 255) / 256, 256, 0, st>>>(update_switch.p, S, 1);  // init_buff.m:41
+  count_launch(ctx);
+  const size_t per = (size_t)d.R_d * d.LDF;
+  int blocks = (int)((per * S + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  broadcast_kernel<<<blocks, 256, 0, st>>>(Bd_fix.p, Bd0.p, per, S);
+  count_launch(ctx);
+  Bd1.zero(st);
+  if (Ad_blk.n) SN_CUDA(cudaMemcpyAsync(Ad_blk.p, Ad_init.p, Ad_blk.n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  check_launch(ctx, "state reset");
+}
+
+SlotState SlotBuffers::view() const {
+  SlotState v{};
+  v.S = S;
+  v.Bx = Bx.p;
+  v.Bd_fix = Bd_fix.p;
+  v.bdfix_stride = 0;
+  v.Bd[0] = Bd0.p; v.Bd[1] = Bd1.p;
+  v.bd_sel = bd_sel.p;
+  v.Ad_blk = Ad_blk.p; v.lam_blk = lam_blk.p; v.ring_head = ring_head.p; v.r_blk = r_blk.p;
+  v.lambda_dav = lambda_dav.p; v.Xm_tilde_prev = Xm_tilde_prev.p; v.update_switch = update_switch.p;
+  v.A = A.p; v.Xhat = Xhat.p; v.Dhat = Dhat.p; v.Q = Q.p; v.G = G.p;
+  v.h_iters = h_iters.p; v.h_cost = h_cost.p; v.gated = gated.p; v.do_update = do_update.p; v.n_up = n_up.p;
+  v.idx_up = idx_up.p; v.idx_rem = idx_rem.p; v.w_iters = w_iters.p; v.err_flag = err_flag.p;
+  v.l_offset = l_offset.p; v.n_hops = n_hops.p; v.frame_base = frame_base.p;
+  v.stats = stats.p;
+  return v;
+}
+
+}  // namespace snmfnat

@@ -1,0 +1,42 @@
+// Owner of the device-resident per-slot state (the struct g of src/init_buff.m for S streams) and the
+// translation of snmfnat_params into kernel-side dimension / scalar blocks.
+#pragma once
+#include "online.cuh"
+#include "stft.cuh"
+
+namespace snmfnat {
+
+struct Config {
+  snmfnat_params p;
+  OnlineDims d;
+  OnlineScalars sc;
+  StftGeom g;
+};
+// Validates p against what the IS16 frame function supports and fills the kernel-side blocks.
+void make_config(snmfnat_ctx* ctx, const snmfnat_params& p, int n2, Config& cfg);
+
+struct SlotBuffers {
+  int S = 0;
+  OnlineDims d{};
+  DevBuf<double> Bx, Bd_fix, Bd0, Bd1, Ad_blk, Ad_init, lam_blk, r_blk, lambda_dav, Xm_tilde_prev;
+  DevBuf<double> A, Xhat, Dhat, Q, G, h_cost, h_init, win_stft, win_istft;
+  DevBuf<int> bd_sel, ring_head, update_switch, h_iters, gated, do_update, n_up, idx_up, idx_rem, w_iters, err_flag;
+  DevBuf<int> l_offset, n_hops;
+  DevBuf<long long> frame_base;
+  DevBuf<unsigned long long> stats;
+
+  void alloc(int S, const OnlineDims& d);
+  // bases are host column-major F x R doubles
+  void set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B_d);
+  // Ad_blk_init: R_a x m_a column-major per slot, `stride` doubles apart (0 = shared); order[s] = source index
+  void set_ad_init(snmfnat_ctx* ctx, const double* Ad_blk_init, int64_t stride, const std::vector<int>& order);
+  // reset every slot to init_buff (src/init_buff.m:17-62): zero histories, Bd <- B_d, Ad_blk <- init
+  void reset(snmfnat_ctx* ctx);
+  SlotState view() const;
+};
+
+// host column-major F x R  <->  device [R][LDF]
+void upload_basis(snmfnat_ctx* ctx, const double* host, int F, int R, int LDF, double* dev);
+void download_basis(snmfnat_ctx* ctx, const double* dev, int F, int R, int LDF, double* host);
+
+}  // namespace snmfnat

@@ -1,0 +1,65 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads and exports every symbol include/snmfnat.h
+declares; the host-side parameter marshalling matches the shipped settings.  No compute calls (no GPU here)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from se_snmf_nat_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    txt = (ROOT / "include" / "snmfnat.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(snmfnat_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from se_snmf_nat_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/snmfnat.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.snmfnat_version() == 100
+
+
+def test_params_default_matches_shipped_settings(lib):
+    from se_snmf_nat_b200 import api
+    from oracle import snmf_oracle as O
+    p = api.default_p()
+    po = O.default_params()
+    for k in ("framelength", "frameshift", "fftlength", "delay", "R_x", "R_d", "R_a", "m_a", "init_N_len",
+              "P_len_k", "P_len_l", "blk_gap", "DCbin", "DCbin_back", "max_iter", "overlapscale", "pow",
+              "nonzerofloor", "overlap_m_a", "Ar_up", "alpha_p", "preemph", "sparsity", "conv_eps", "alpha_eta",
+              "alpha_d", "beta", "beta_max"):
+        assert p[k] == po[k], k
+    assert np.allclose(p["win_STFT"], po["win_STFT"], atol=0, rtol=0)
+    ps = api.params_struct(dict(p, ENHANCE_METHOD="Wiener", EVENT_NUM=3, EVENT_RANK=[1, 21, 41], cf="is"))
+    assert ps.ENHANCE_METHOD == 1 and list(ps.EVENT_RANK)[:3] == [1, 21, 41] and ps.cf == 0
+
+
+def test_no_device_fails_loudly(lib):
+    """On a box without a GPU context creation must fail with ENODEVICE -- never fall back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from se_snmf_nat_b200 import api
+    with pytest.raises(api.SnmfnatError) as e:
+        api.Context(0)
+    assert e.value.code == -2
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    for f in (ROOT / "se_snmf_nat_b200").rglob("*.py"):
+        assert "oracle" not in f.read_text().replace("no oracle", ""), f

@@ -1,0 +1,125 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the float64 oracle on identical inputs.
+
+Tolerances are the ones BASELINE.json:north_star states: H/W and enhanced spectra relative error <= 1e-3,
+waveform SNR >= 40 dB.  The float64 kernels normally agree to ~1e-10; iteration counts and gates must be equal.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err, snr_db
+
+pytestmark = pytest.mark.gpu
+
+SPEC_TOL = 1e-3     # north_star: spectra / activations relative error
+WAVE_SNR_DB = 40.0  # north_star: waveform SNR
+
+
+@pytest.fixture(scope="module")
+def api():
+    from se_snmf_nat_b200 import api as a
+    return a
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import snmf_oracle
+    return snmf_oracle
+
+
+def run_gpu_traced(api, p, pcms, bases, h_init, Ad, **kw):
+    ctx = api.get_context(0)
+    b = api.Batch(ctx, p, bases["B_DFT_x"], bases["B_DFT_d"], [len(x) for x in pcms], h_init, Ad, **kw)
+    b.enable_trace(True)
+    b.upload(pcms)
+    b.run()
+    outs = b.download()
+    return b, outs
+
+
+def test_m03_full_parity(api, O, bases, wavs, rng_inputs, m03_oracle):
+    """config 1: filewise_run_IS16 on wav/M03_423C0213_STR.CH6.wav with the shipped dictionaries."""
+    h_init, Ad = rng_inputs
+    p = api.default_p()
+    b, outs = run_gpu_traced(api, p, [wavs["M03_in"]], bases, h_init, Ad)
+    out = outs[0]
+    ref = m03_oracle
+    assert len(out) == len(ref["out"]) == 55040
+    hi = b.trace(0, "h_iters").astype(int)
+    first_bad = np.flatnonzero(hi != ref["h_iters"])
+    assert first_bad.size == 0, f"H-solve iteration counts diverge first at hop {first_bad[:1]}"
+    assert np.array_equal(b.trace(0, "gated").astype(int), ref["gated"].astype(int))
+    assert np.array_equal(b.trace(0, "R_a_up").astype(int), ref["R_a_up"])
+    assert np.array_equal(b.trace(0, "w_iters").astype(int), ref["w_iters"])
+    A = b.trace(0, "A")
+    Xt = b.trace(0, "Xm_tilde")
+    worstA = max(rel_err(ref["A"][i], A[i]) for i in range(len(hi)))
+    worstX = max(rel_err(ref["Xm_tilde"][i], Xt[i]) for i in range(len(hi)))
+    assert worstA <= SPEC_TOL, worstA
+    assert worstX <= SPEC_TOL, worstX
+    assert rel_err(ref["B_DFT_d_final"], b.noise_basis(0)) <= SPEC_TOL
+    assert snr_db(ref["out"], out) >= WAVE_SNR_DB
+    # against the reference's own shipped output: the coarse end-to-end pin
+    assert snr_db(wavs["M03_ref_out"], out) > 20.0
+    st = b.stats()
+    assert st["hops"] == len(hi) and st["h_iters"] == int(ref["h_iters"].sum())
+    assert st["w_iters"] == int(ref["w_iters"].sum())
+    print(f"M03: worst rel err A {worstA:.2e}, Xm_tilde {worstX:.2e}, SNR vs oracle {snr_db(ref['out'], out):.1f} dB")
+    b.close()
+
+
+def test_ragged_batch_equals_single_runs(api, O, bases, wavs, rng_inputs):
+    """Utterances of different length (including empty and shorter than one hop) in one batch give exactly what
+    each gives alone, and what the oracle gives."""
+    h_init, Ad = rng_inputs
+    p = api.default_p()
+    po = O.default_params()
+    rs = np.random.RandomState(7)
+    m04 = wavs["M04_in"]
+    pcms = [m04[:16000], np.zeros(0, np.int16), m04[5000:5100], m04[20000:20000 + 160 * 37 + 13],
+            (rs.randn(8000) * 3000).astype(np.int16)]
+    ads = np.stack([rs.rand(50, 100) for _ in pcms])
+    outs = api.enhance_batch(pcms, p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=ads)
+    for i, pcm in enumerate(pcms):
+        ref, _ = O.enhance_utterance(pcm, po, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=ads[i])
+        assert len(outs[i]) == len(ref) == (len(pcm) // 160 + 1) * 160
+        assert np.abs(outs[i].astype(int) - ref.astype(int)).max() <= 1, i
+        alone = api.enhance_batch([pcm], p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=ads[i])[0]
+        assert np.array_equal(alone, outs[i]), "batch composition changed a result"
+
+
+@pytest.mark.parametrize("variant", ["wiener", "no_adapt", "no_blk", "maxiter25_gap5", "preemph", "R_a20_ma40"])
+def test_settings_variants(api, O, bases, wavs, rng_inputs, variant):
+    """The knobs the reference's settings/bak_IS16_results variants change are runtime parameters."""
+    h_init, Ad = rng_inputs
+    over = {
+        "wiener": dict(ENHANCE_METHOD="Wiener"),
+        "no_adapt": dict(adapt_train_N=0),
+        "no_blk": dict(blk_sparse=0),
+        "maxiter25_gap5": dict(max_iter=25, blk_gap=5),
+        "preemph": dict(preemph=0.92),
+        "R_a20_ma40": dict(R_a=20, m_a=40),
+    }[variant]
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    if variant == "R_a20_ma40":
+        Ad = np.random.RandomState(11).rand(20, 40)
+    pcm = wavs["M03_in"][8000:8000 + 160 * 120]
+    out = api.enhance_batch([pcm], p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad)[0]
+    ref, _ = O.enhance_utterance(pcm, po, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad)
+    assert len(out) == len(ref)
+    assert snr_db(ref, out) >= WAVE_SNR_DB
+    assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1
+
+
+def test_unsupported_configs_fail_loudly(api, bases, rng_inputs):
+    h_init, Ad = rng_inputs
+    for over in (dict(Splice=1), dict(blk_len_sep=2, blk_hop_sep=2)):
+        with pytest.raises(api.SnmfnatError) as e:
+            api.enhance_batch([np.zeros(1000, np.int16)], dict(api.default_p(), **over), bases["B_DFT_x"],
+                              bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad)
+        assert e.value.code == -4
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
