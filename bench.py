@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its quoted configuration.
+
+Metric: enhanced audio-seconds per wall-second (xRT) of the IS16 SNMF-NAT pipeline on a CHiME-4-shaped batch of
+1024 synthetic 16 kHz utterances per GPU (BASELINE.json configs[2]); weak scaling: every rank enhances its own
+1024-utterance batch, no data-path collective.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--utts U] [--impl ours|reference]
+
+A "step" is one pass of the whole hot path (STFT -> per-hop {H-solve, gain, W-solve} -> ISTFT/OLA) over the batch.
+`value` has the PCM already resident in HBM; `e2e` goes through the public C-ABI call sequence with pinned HOST
+buffers (H2D of the PCM and D2H of the enhanced PCM inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+FS = 16000
+METRIC = "xRT: enhanced audio-seconds per second (IS16 SNMF-NAT, CHiME-4-shaped batch)"
+UNIT = "audio-s/s"
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference leg
+def _cpu_worker(args):
+    """One oracle process: enhance one cropped utterance on one core (the oracle is the float64 NumPy restatement of
+    the reference's MATLAB code; MATLAB/Octave are not available on the box)."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    idx, pcm, ad = args
+    from oracle import snmf_oracle as O
+    import bench_workload as W
+    fx = W.load_fixtures()
+    p = O.default_params()
+    t0 = time.perf_counter()
+    out, _ = O.enhance_utterance(pcm, p, fx["B_x"], fx["B_d"], h_init=fx["h_init"], Ad_blk_init=ad)
+    return idx, len(pcm) / FS, time.perf_counter() - t0, int(np.abs(out.astype(np.int64)).sum())
+
+
+def _cpu_warm(i):
+    from oracle import snmf_oracle as O  # noqa: F401
+    import bench_workload as W
+    W.load_fixtures()
+    return i
+
+
+def cpu_reference_pass(pcms, ads, n_procs, crop_s):
+    """Enhance the first `n_procs` utterances (cropped to crop_s seconds) with one oracle process per host core.
+    Returns (audio seconds, wall seconds)."""
+    import multiprocessing as mp
+    jobs = []
+    for i in range(n_procs):
+        u = i % len(pcms)
+        jobs.append((i, np.ascontiguousarray(pcms[u][: int(crop_s * FS)]), ads[u]))
+    ctx = mp.get_context("spawn")
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:  # one BLAS thread per worker: the children read these when they import numpy
+        os.environ[k] = "1"
+    try:
+        with ctx.Pool(n_procs) as pool:
+            pool.map(_cpu_warm, range(n_procs))      # import numpy/scipy and load fixtures outside the timed region
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, jobs, chunksize=1)
+            wall = time.perf_counter() - t0
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    audio = sum(r[1] for r in res)
+    return audio, wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+        self.t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ peaks
+def measured_peaks():
+    pk = {}
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        pk.update(json.loads(f.read_text()))
+        pk["_hbm_source"] = "measured (MEASURED_PEAKS.json)"
+    else:
+        pk["hbm_gbs"] = 6650.0
+        pk["_hbm_source"] = "fallback (B200_PROFILING.md)"
+    exe = ROOT / "tools" / "peaks_fp64"
+    try:
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout
+        pk["fp64"] = json.loads(out.strip().splitlines()[-1])
+        pk["_fp64_source"] = "measured live by tools/peaks_fp64 (DFMA / FP64 mma.sync issue-rate microbenchmark)"
+    except Exception:
+        pk["fp64"] = {"dfma_tflops": 36.5, "dmma_tflops": 37.16}
+        pk["_fp64_source"] = "recorded on this pool (profiles/peaks_fp64_r01.json)"
+    return pk
+
+
+# ------------------------------------------------------------------------------------------------ main arms
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path (the oracle port: MATLAB/Octave are not
+    installed) on all host cores, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import bench_workload as W
+    cores = min(host_cores(), 64)
+    crop = 3.0
+    pcms, ads, _ = W.make_batch(cores, rank=0, max_seconds=crop)
+    pcms = [p if len(p) >= crop * FS else np.resize(p, int(crop * FS)) for p in pcms]
+    times, audio = [], 0.0
+    for i in range(args.warmup_ref + args.steps):
+        a, w = cpu_reference_pass(pcms, ads, cores, crop)
+        if i >= args.warmup_ref:
+            times.append(w)
+            audio = a
+    ms = 1e3 * float(np.mean(times))
+    val = audio / (ms / 1e3)
+    sample = f"{cores} utterances x {crop:.0f} s of the same synthetic batch, one oracle process per core"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup_ref, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Do_MultiBatch_IS16 CHiME-4-shaped batch (configs[2]), bounded CPU sample",
+                   "sample": sample, "settings": "initial_setting_SNMF_NAT (shipped)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import bench_workload as W
+    from se_snmf_nat_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsnmfnat has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- workload (synthesised on the GPU with torch: input generation is not part of the measured path)
+    t_gen = time.perf_counter()
+    pcms, ads, fx = W.make_batch(args.utts, rank=rank, device=dev)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    lens = np.array([len(x) for x in pcms], dtype=np.int64)
+    audio_s = float(lens.sum()) / FS
+    p = api.default_p()
+    ctx = api.Context(local_rank)
+    batch = api.Batch(ctx, p, fx["B_x"], fx["B_d"], lens, fx["h_init"], ads)
+    # pinned host buffers: packed PCM in, packed PCM out
+    pin_in = torch.empty(int(lens.sum()), dtype=torch.int16).pin_memory()
+    pin_in.numpy()[:] = np.concatenate(pcms)
+    out_total = int(batch.out_lengths.sum())
+    pin_out = torch.empty(out_total, dtype=torch.int16).pin_memory()
+    stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+
+    batch.upload_packed(pin_in.data_ptr())
+    ctx.sync()
+    batch.set_profile(True)
+    for _ in range(args.warmup):
+        batch.run()
+    ctx.sync()
+
+    # ---- timed: device-resident
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count
+    barrier(); torch.cuda.synchronize(); ctx.sync()
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        batch.run()
+    e1.record(stream)
+    ctx.sync(); torch.cuda.synchronize(); barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - l0
+    ms_total = max_over_ranks(float(e0.elapsed_time(e1)))
+    ms_step = ms_total / args.steps
+    total_audio = sum_over_ranks(audio_s)
+    value = total_audio / (ms_step / 1e3)
+    prof = batch.profile()
+    stats = batch.stats()
+
+    # ---- timed: end to end through the C ABI with host buffers (H2D + run + D2H every step)
+    barrier(); torch.cuda.synchronize(); ctx.sync()
+    t0 = time.perf_counter()
+    e2 = torch.cuda.Event(enable_timing=True)
+    e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        batch.upload_packed(pin_in.data_ptr())
+        batch.run()
+        batch.download_packed(pin_out.data_ptr())   # synchronises (reads the error flag back)
+    e3.record(stream)
+    ctx.sync(); torch.cuda.synchronize(); barrier()
+    wall_e2e = time.perf_counter() - t0
+    ms_e2e = max_over_ranks(max(float(e2.elapsed_time(e3)), 1e3 * wall_e2e)) / args.steps
+    e2e_value = total_audio / (ms_e2e / 1e3)
+    checksum = int(np.abs(pin_out.numpy().astype(np.int64)).sum())
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel class (device time from CUDA events on the launch stream)
+    pk = measured_peaks()
+    F, R, m_a = 513, 200, 100
+    mean_rup = stats["w_atoms"] / max(stats["w_solves"], 1)
+    fl_h = stats["h_iters"] * (4.0 * F * R + 10.0 * F)
+    fl_w = stats["w_iters"] * (4.0 * F * mean_rup * m_a + 12.0 * F * m_a)
+    nf = stats["hops"]
+    by_stft = nf * (2.0 * 160 + 1024 * 8 * 2 + 513 * 16 * 2 + 513 * 8)         # pcm in, frames w+r (cuFFT), Y w+r, Ym w
+    by_istft = nf * (513 * 16 * 2 + 513 * 8 + 513 * 16 + 1024 * 8 * 2 + 2.0 * 160)
+    classes = {
+        "hsolve": {"bound": "fp64", "work": fl_h, "peak": pk["fp64"]["dfma_tflops"], "unit": "TFLOP/s"},
+        "wsolve": {"bound": "tensor", "work": fl_w, "peak": pk["fp64"]["dmma_tflops"], "unit": "TFLOP/s"},
+        "stft": {"bound": "hbm", "work": by_stft, "peak": pk["hbm_gbs"], "unit": "GB/s"},
+        "istft": {"bound": "hbm", "work": by_istft, "peak": pk["hbm_gbs"], "unit": "GB/s"},
+    }
+    roof_all = {}
+    for name, c in classes.items():
+        ms = prof[name]["ms"]
+        n_l = max(prof[name]["launches"], 1)
+        scale = 1e9 if c["unit"] == "TFLOP/s" else 1e6
+        ach = c["work"] / ms / scale if ms > 0 else 0.0
+        roof_all[name] = {"bound": c["bound"], "achieved": ach, "peak": c["peak"], "unit": c["unit"],
+                          "frac": ach / c["peak"], "ms_per_step": ms, "launches": n_l,
+                          "avg_launch_ms": ms / n_l, "share_of_step": ms / prof["total"]["ms"],
+                          "work_per_launch": c["work"] / n_l}
+    roof_all["gain"] = {"ms_per_step": prof["gain"]["ms"], "launches": prof["gain"]["launches"],
+                        "share_of_step": prof["gain"]["ms"] / prof["total"]["ms"]}
+    dom = max(("hsolve", "wsolve", "stft", "istft"), key=lambda k: roof_all[k]["ms_per_step"])
+    roofline = dict(roof_all[dom])
+    roofline.update({"kernel": dom + "_kernel", "traffic": None,
+                     "peak_source": pk["_fp64_source"] if roofline["unit"] == "TFLOP/s" else pk["_hbm_source"],
+                     "note": "fp64 = FP64 FMA pipe (DFMA issue rate); tensor = FP64 tensor-core mma.sync m8n8k4 "
+                             "(MEASURED_PEAKS.json holds no FP64 figure, so the FP64 peaks are measured by "
+                             "tools/peaks_fp64); achieved = SURVEY.md 8(d) algorithmic flops / CUDA-event time"})
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = min(host_cores(), 64)
+        crop = 3.0
+        sub = [x[: int(crop * FS)] if len(x) >= crop * FS else np.resize(x, int(crop * FS)) for x in pcms[:cores]]
+        a, w = cpu_reference_pass(sub, ads, cores, crop)
+        cpu = {"value": a / w, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} utterances x {crop:.0f} s of this batch, one float64 NumPy oracle process per core "
+                         f"(MATLAB/Octave not installed)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "Do_MultiBatch_IS16 CHiME-4-shaped batch (BASELINE.json configs[2]): "
+                               f"{args.utts} synthetic 16 kHz utterances per GPU, U[3,12] s, filewise semantics",
+                   "utterances_per_gpu": args.utts, "audio_s_per_gpu": audio_s, "hops_per_gpu": int(nf),
+                   "settings": "initial_setting_SNMF_NAT (shipped): F=513 R_x=R_d=100 R_a=50 m_a=100 max_iter=100",
+                   "l2": "per-step working set (frame arrays + per-stream state, ~21 GB) is far larger than the "
+                         "126 MB L2; no explicit flush needed",
+                   "parallelism": f"utterance-sharded x{world}, no collectives"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(lens.sum()) * 2,
+                "d2h_bytes_per_step": out_total * 2, "api": "snmfnat_batch_upload_packed + snmfnat_batch_run + "
+                                                            "snmfnat_batch_download_packed (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "roofline_all": roof_all,
+        "cpu_baseline": cpu,
+        "mu_iters_per_s": (stats["h_iters"] + stats["w_iters"]) * world / (ms_step / 1e3),
+        "stats": {k: stats[k] for k in ("hops", "h_iters", "w_iters", "gated_hops", "w_solves", "w_atoms", "launches")},
+        "algorithmic_tflops": stats["flops"] * world / (ms_step / 1e3) / 1e12,
+        "output_checksum": checksum, "workload_gen_s": t_gen,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--utts", type=int, default=1024)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup_ref = min(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

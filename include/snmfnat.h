@@ -216,6 +216,11 @@ int snmfnat_batch_get_stats(snmfnat_batch* b, snmfnat_batch_stats* out);
  * "R_a_up","w_iters"}; only available when tracing was enabled before the run. */
 int snmfnat_batch_enable_trace(snmfnat_batch* b, int on);
 int snmfnat_batch_get_trace(snmfnat_batch* b, int u, const char* what, double* buf, int64_t n);
+/* Per-kernel-class device times of the last run, measured with CUDA events recorded on the context stream
+ * around every launch (enable before the run).  ms[0..5] = STFT (framing + cuFFT + epilogue), H-solve,
+ * gain/blk_sparse, W-solve, ISTFT + overlap-add, whole run; counts[0..5] = launches of each class. */
+int snmfnat_batch_set_profile(snmfnat_batch* b, int on);
+int snmfnat_batch_get_profile(snmfnat_batch* b, double* ms6, int64_t* counts6);
 /* Final adapted noise basis of utterance u (n2 x R_d), i.e. g.B_DFT_d after the last hop. */
 int snmfnat_batch_get_noise_basis(snmfnat_batch* b, int u, double* B_d);
 

@@ -233,6 +233,17 @@ class Batch:
     def download_packed(self, packed_ptr: int):
         check(self._lib.snmfnat_batch_download_packed(self._h, C.cast(packed_ptr, C.POINTER(C.c_int16))))
 
+    def set_profile(self, on=True):
+        check(self._lib.snmfnat_batch_set_profile(self._h, 1 if on else 0))
+
+    def profile(self) -> dict:
+        """Device time (ms) per kernel class of the last run, from CUDA events on the launch stream."""
+        ms = (C.c_double * 6)()
+        cnt = (C.c_int64 * 6)()
+        check(self._lib.snmfnat_batch_get_profile(self._h, ms, cnt))
+        names = ["stft", "hsolve", "gain", "wsolve", "istft", "total"]
+        return {n: {"ms": ms[i], "launches": int(cnt[i])} for i, n in enumerate(names)}
+
     def stats(self) -> dict:
         s = BatchStats()
         check(self._lib.snmfnat_batch_get_stats(self._h, C.byref(s)))

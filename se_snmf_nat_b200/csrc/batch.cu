@@ -33,6 +33,14 @@ struct snmfnat_batch {
   bool trace = false, uploaded = false, ran = false;
   FftPlans fft;
   int64_t launches_last = 0;
+  // profiling: events around every launch of the hop loop
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;
+  double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+  int64_t prof_cnt[6] = {0, 0, 0, 0, 0, 0};
+  ~snmfnat_batch() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
 };
 
 static UttTables utt_tables(const snmfnat_batch* b) {
@@ -195,12 +203,27 @@ int snmfnat_batch_run(snmfnat_batch* b) {
   SN_CUDA(cudaSetDevice(ctx->device));
   const Config& c = b->cfg;
   const int64_t l0 = ctx->launches;
+  const bool prof = b->profile;
+  size_t evi = 0;
+  if (prof) {
+    const size_t need = 3 * (size_t)b->max_hops + 8;
+    while (b->ev.size() < need) {
+      cudaEvent_t e;
+      SN_CUDA(cudaEventCreate(&e));
+      b->ev.push_back(e);
+    }
+  }
+  auto mark = [&]() {
+    if (prof) SN_CUDA(cudaEventRecord(b->ev[evi++], ctx->stream));
+  };
+  mark();  // 0: start
   b->sb.reset(ctx);
   const UttTables ut = utt_tables(b);
   // STFT of every frame
   launch_frame_pcm(ctx, c.g, ut, b->pcm.p, b->sb.win_stft.p, b->frames.p);
   SN_CUFFT(cufftExecD2Z(b->fft.fwd, b->frames.p, reinterpret_cast<cufftDoubleComplex*>(b->Yc.p)));
   launch_stft_post(ctx, c.g, b->Yc.p, b->NF, b->Ym.p, nullptr);
+  mark();  // 1: STFT done
   // hop loop
   const SlotState st = b->sb.view();
   FrameArrays fr{b->Ym.p, b->Xt.p};
@@ -209,8 +232,11 @@ int snmfnat_batch_run(snmfnat_batch* b) {
   for (int g = 0; g < b->max_hops; ++g) {
     const int na = b->active_at[g];
     launch_hsolve(ctx, c.d, c.sc, st, fr, b->sb.h_init.p, na, g);
+    mark();
     launch_gain(ctx, c.d, c.sc, st, fr, trp, na, g);
+    mark();
     launch_wsolve(ctx, c.d, c.sc, st, trp, na, g);
+    mark();
   }
   // ISTFT + overlap-add
   launch_istft_pre(ctx, c.g, b->Yc.p, b->Xt.p, b->NF);
@@ -221,6 +247,7 @@ int snmfnat_batch_run(snmfnat_batch* b) {
     windowed = 1;
   }
   launch_ola_int16(ctx, c.g, ut, b->frames.p, b->sb.win_istft.p, windowed, b->out.p);
+  mark();  // end
   b->launches_last = ctx->launches - l0;
   b->ran = true;
   SN_API_END
@@ -286,6 +313,47 @@ int snmfnat_batch_get_stats(snmfnat_batch* b, snmfnat_batch_stats* out) {
   out->flops = (double)s[1] * (4.0 * F * R + 10.0 * F) + (double)s[2] * (4.0 * F * mean_rup * ma + 12.0 * F * ma) +
                (double)s[0] * 0.7e6;
   out->launches = b->launches_last;
+  SN_API_END
+}
+
+int snmfnat_batch_set_profile(snmfnat_batch* b, int on) {
+  SN_API_BEGIN
+  SN_REQUIRE(b, SNMFNAT_EINVAL, "NULL argument");
+  b->profile = on != 0;
+  SN_API_END
+}
+
+int snmfnat_batch_get_profile(snmfnat_batch* b, double* ms6, int64_t* counts6) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && ms6, SNMFNAT_EINVAL, "NULL argument");
+  SN_REQUIRE(b->profile && b->ran, SNMFNAT_EINVAL, "profiling was not enabled for the last run");
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  SN_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  const size_t n = 3 * (size_t)b->max_hops + 3;
+  double ms[6] = {0, 0, 0, 0, 0, 0};
+  int64_t cnt[6] = {0, 0, 0, 0, 0, 0};
+  auto el = [&](size_t a, size_t q) {
+    float t = 0.f;
+    SN_CUDA(cudaEventElapsedTime(&t, b->ev[a], b->ev[q]));
+    return (double)t;
+  };
+  ms[0] = el(0, 1);
+  cnt[0] = 3;
+  for (int g = 0; g < b->max_hops; ++g) {
+    const size_t e0 = 1 + 3 * (size_t)g;
+    ms[1] += el(e0, e0 + 1);
+    ms[2] += el(e0 + 1, e0 + 2);
+    ms[3] += el(e0 + 2, e0 + 3);
+    cnt[1]++; cnt[2]++; cnt[3]++;
+  }
+  ms[4] = el(n - 2, n - 1);
+  cnt[4] = 3;
+  ms[5] = el(0, n - 1);
+  cnt[5] = b->launches_last;
+  for (int i = 0; i < 6; ++i) {
+    ms6[i] = ms[i];
+    if (counts6) counts6[i] = cnt[i];
+  }
   SN_API_END
 }
 
