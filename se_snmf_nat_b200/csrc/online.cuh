@@ -88,6 +88,15 @@ void launch_gain(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc,
 // W-solve (noise-basis adaptation) for the slots whose do_update flag is set.
 void launch_wsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const TraceArrays* tr, int n_active, int g_step);
+// fast paths for the shipped geometry (online_fast.cu); the launchers above dispatch to them when supported
+bool hsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d);
+void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                        const FrameArrays& fr, const double* h_init, int n_active, int g_step);
+bool wsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d);
+void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                        const TraceArrays* tr, int n_active, int g_step);
+// SNMFNAT_FORCE_GENERIC=1 in the environment disables the fast paths (used by the parity tests)
+bool force_generic();
 // shared-memory footprints (bytes) so that callers can reject configurations that do not fit
 size_t hsolve_smem_bytes(const OnlineDims& d);
 size_t wsolve_smem_bytes(const OnlineDims& d);

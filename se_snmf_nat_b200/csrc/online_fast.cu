@@ -1,0 +1,737 @@
+// Second-generation per-hop MU kernels for the shipped geometry (fftlength 1024 -> F = 513 rows).
+//
+// hsolve_fast_kernel : 4-CTA cluster per stream, 16 warps per CTA.  Each CTA keeps 128 rows of W = [B_x B_d] in
+//   shared memory with an XOR swizzle, element (k,f) at k*128 + (f ^ (k & 15)), so that BOTH directions of the
+//   mat-vec pair are bank-conflict free without any cross-lane reduction:
+//     lambda = W h   : lanes <-> rows   (one column k per step, h_k broadcast)
+//     g = W'(v./lambda): lanes <-> atoms (one row pair per step, ratio broadcast)
+//   The F - 512 tail rows (the Nyquist bin for F = 513) live in a small row-major side array on the last rank.
+//   Per MU iteration: 3 block barriers + 1 cluster barrier; the R-vector g, the cost partial and the tail
+//   terms travel through distributed shared memory.
+//
+// wsolve_fast_kernel : 4-CTA cluster per stream, 17 warps per CTA, one 8-row FP64 tensor-core tile per warp
+//   (mma.sync m8n8k4.f64).  W and G = (V./Lambda) H' fragments stay in registers for the whole solve in the SAME
+//   fragment layout (the k order of the first GEMM is permuted to match the accumulator layout of the second), the
+//   CTA's slice of V = lambda_d_blk is staged once in shared memory, H is staged once.  Padding rows/columns are
+//   neutral by construction (V pad = floor, W pad = 0, H pad = 0) so the inner loops carry no predicates.
+//   v./lambda uses a Newton reciprocal and the KL cost a table-driven log (|err| < 4e-16 absolute).
+#include <cooperative_groups.h>
+#include <cmath>
+#include "online.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace snmfnat {
+
+// =====================================================================================================
+// shared helpers
+// =====================================================================================================
+__device__ __forceinline__ double fast_rcp(double x) {  // x > 0, normal.  <= 1 ulp after two Newton steps
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// log(x) for positive normal x: x = 2^e * m, m in [1,2); c = centre of m's 1/128 bucket; z = m/c - 1, |z| <= 2^-8;
+// log x = e ln2 + log c + log1p(z) with a degree-7 series.  tab[i] = {1/c_i, log c_i}.
+__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
+  const int hi = __double2hiint(x);
+  const int e = (hi >> 20) - 1023;
+  const int idx = (hi >> 13) & 127;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 t = tab[idx];
+  const double z = fma(m, t.x, -1.0);
+  double p = fma(z, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(p, z, 0.2);
+  p = fma(p, z, -0.25);
+  p = fma(p, z, 1.0 / 3.0);
+  p = fma(p, z, -0.5);
+  const double l = fma(p, z * z, z);
+  return fma((double)e, 0.693147180559945309417232, t.y + l);
+}
+
+__global__ void log_table_kernel(double2* tab) {
+  const int i = threadIdx.x;
+  if (i < 128) {
+    const double c = 1.0 + (i + 0.5) / 128.0;
+    tab[i] = make_double2(1.0 / c, log(c));
+  }
+}
+
+static double2* g_log_tab[64] = {nullptr};
+static const double2* log_table(snmfnat_ctx* ctx) {
+  const int dev = ctx->device;
+  SN_REQUIRE(dev >= 0 && dev < 64, SNMFNAT_EINVAL, "device index out of range");
+  if (!g_log_tab[dev]) {
+    double2* p = nullptr;
+    SN_CUDA(cudaMalloc(&p, 128 * sizeof(double2)));
+    log_table_kernel<<<1, 128, 0, ctx->stream>>>(p);
+    count_launch(ctx);
+    SN_CUDA(cudaStreamSynchronize(ctx->stream));
+    g_log_tab[dev] = p;
+  }
+  return g_log_tab[dev];
+}
+
+// =====================================================================================================
+// H-solve, fast path: F = 512 + E (0 <= E <= 8)
+// =====================================================================================================
+constexpr int HF_THREADS = 512;
+constexpr int HF_WARPS = 16;
+constexpr int HF_CL = 4;
+constexpr int HF_ROWS = 128;   // rows per CTA
+constexpr int HF_KG = 8;       // k groups in the lambda pass
+
+struct HfLayout {
+  int E, XN;
+  size_t off_W, off_Wt, off_v, off_r, off_rsw, off_lam, off_h, off_dph, off_wn, off_xch, off_misc, bytes;
+};
+__host__ __device__ inline HfLayout hf_layout(int F, int R) {
+  HfLayout L;
+  L.E = F - HF_CL * HF_ROWS;
+  L.XN = R + 8;
+  size_t o = 0;
+  L.off_W = o;    o += (size_t)R * HF_ROWS;
+  L.off_Wt = o;   o += (size_t)(L.E > 0 ? L.E : 0) * R;
+  o = (o + 1) & ~(size_t)1;
+  L.off_v = o;    o += HF_ROWS + 8;
+  L.off_r = o;    o += HF_ROWS + 8;
+  L.off_rsw = o;  o += HF_ROWS + 8;
+  L.off_lam = o;  o += (size_t)HF_KG * HF_ROWS;
+  L.off_h = o;    o += R;
+  L.off_dph = o;  o += R;
+  L.off_wn = o;   o += R;
+  o = (o + 1) & ~(size_t)1;
+  L.off_xch = o;  o += 2 * (size_t)L.XN;
+  L.off_misc = o; o += 48;
+  L.bytes = o * sizeof(double);
+  return L;
+}
+
+__global__ void __cluster_dims__(HF_CL, 1, 1) __launch_bounds__(HF_THREADS, 1)
+hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, const double* __restrict__ h_init,
+                   int g_step) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int slot = blockIdx.x / HF_CL;
+  const int l = g_step + 1 - st.l_offset[slot];
+  if (l < 1 || l > st.n_hops[slot]) return;  // uniform over the cluster
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = d.F, R = d.R, R1 = d.R_x, LDF = d.LDF;
+  const HfLayout L = hf_layout(F, R);
+  const int E = L.E;
+  const bool tail_rank = (rank == HF_CL - 1) && E > 0;
+  const int f0 = rank * HF_ROWS;
+
+  extern __shared__ __align__(16) double smem[];
+  double* Ws = smem + L.off_W;
+  double* Wt = smem + L.off_Wt;       // [E][R] tail rows (last rank only)
+  double* v_s = smem + L.off_v;       // [128 + E]
+  double* r_s = smem + L.off_r;       // ratio v./lambda
+  double* r_sw = smem + L.off_rsw;    // r_sw[f] = r_s[f ^ 1]
+  double* lam_part = smem + L.off_lam;
+  double* h_s = smem + L.off_h;
+  double* dph_s = smem + L.off_dph;
+  double* wn_s = smem + L.off_wn;
+  double* xch = smem + L.off_xch;     // [2][R + 8]: g partial, [R] = cost partial
+  double* misc = smem + L.off_misc;   // [0..7] cost partials per warp, [8] hsum, [16..23] lambda of tail rows
+
+  const double* __restrict__ W1 = st.Bx;
+  const double* __restrict__ W2 = st.Bd[st.bd_sel[slot]] + (size_t)slot * d.R_d * LDF;
+  const long long frame = st.frame_base[slot] + g_step;
+  const double* __restrict__ V = fr.Ym + (size_t)frame * LDF;
+  const double flr = sc.flr;
+
+  // ---- stage W (swizzled), partial column sums / sums of squares over this CTA's rows ----
+  for (int k = warp; k < R; k += HF_WARPS) {
+    const double* src = (k < R1 ? W1 + (size_t)k * LDF : W2 + (size_t)(k - R1) * LDF);
+    double s1 = 0.0, s2 = 0.0;
+    const int sw = k & 15;
+#pragma unroll
+    for (int j = 0; j < HF_ROWS / 32; ++j) {
+      const int f = lane + 32 * j;
+      const double x = src[f0 + f];
+      Ws[(size_t)k * HF_ROWS + (f ^ sw)] = x;
+      s1 += x;
+      s2 = fma(x, x, s2);
+    }
+    if (tail_rank && lane < E) {
+      const double x = src[HF_CL * HF_ROWS + lane];
+      Wt[(size_t)lane * R + k] = x;
+      s1 += x;
+      s2 = fma(x, x, s2);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      xch[k] = s2;  // buffer 0 carries [sumsq | sum] for the normalisation exchange (R + 8 >= ... uses both buffers)
+      xch[L.XN + k] = s1;
+    }
+  }
+  for (int f = tid; f < HF_ROWS + (tail_rank ? E : 0); f += HF_THREADS)
+    v_s[f] = fmax(V[f < HF_ROWS ? f0 + f : HF_CL * HF_ROWS + (f - HF_ROWS)], flr);  // sparse_nmf.m:169
+  cluster.sync();
+
+  // ---- column norms, h scaling (sparse_nmf.m:157-160), denominators (:192-193) ----
+  if (tid < R) {
+    double s2 = 0.0, s1 = 0.0;
+    for (int c = 0; c < HF_CL; ++c) {
+      const double* rx = cluster.map_shared_rank(xch, c);
+      s2 += rx[tid];
+      s1 += rx[L.XN + tid];
+    }
+    const double wn = sqrt(s2);
+    wn_s[tid] = wn;
+    dph_s[tid] = fmax(s1 / wn + sc.sparsity, flr);
+    h_s[tid] = h_init[tid] * wn;
+  }
+  cluster.sync();  // everyone has read both exchange buffers before they are reused; publishes wn_s / h_s
+  for (int k = warp; k < R; k += HF_WARPS) {
+    const double wn = wn_s[k];
+#pragma unroll
+    for (int j = 0; j < HF_ROWS / 32; ++j) {
+      double* p = Ws + (size_t)k * HF_ROWS + lane + 32 * j;
+      *p = *p / wn;
+    }
+    if (tail_rank && lane < E) Wt[(size_t)lane * R + k] = Wt[(size_t)lane * R + k] / wn;
+  }
+  __syncthreads();
+
+  // ---- multiplicative updates ----
+  const int kg = warp & (HF_KG - 1), rh = warp >> 3;   // lambda pass: k group, row half
+  const int kb = warp;                                  // g pass: block of 16 atoms, lanes 16..31 take rows 64..127
+  const int kl = lane & 15, fh = lane >> 4;
+  const int kB = kb * 16 + kl;
+  int it = 0, buf = 0;
+  double last_cost = INFINITY, cost = 0.0;
+  for (;;) {
+    // (A) lambda partials: this warp sums columns k = kg, kg+8, ... for rows rh*64 + lane + {0,32}
+    {
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      const double* base = Ws + rh * 64;
+      const int x0 = lane ^ kg, x1 = lane ^ (kg | 8);
+      int k = kg;
+      for (; k + 8 < R; k += 16) {
+        const double h0 = h_s[k], h1 = h_s[k + 8];
+        const double* w0 = base + (size_t)k * HF_ROWS + x0;
+        const double* w1 = base + (size_t)(k + 8) * HF_ROWS + x1;
+        a0 = fma(w0[0], h0, a0);
+        a1 = fma(w0[32], h0, a1);
+        b0 = fma(w1[0], h1, b0);
+        b1 = fma(w1[32], h1, b1);
+      }
+      if (k < R) {
+        const double h0 = h_s[k];
+        const double* w0 = base + (size_t)k * HF_ROWS + x0;
+        a0 = fma(w0[0], h0, a0);
+        a1 = fma(w0[32], h0, a1);
+      }
+      lam_part[kg * HF_ROWS + rh * 64 + lane] = a0 + b0;
+      lam_part[kg * HF_ROWS + rh * 64 + lane + 32] = a1 + b1;
+      if (tail_rank && warp < E) {  // tail row `warp`: lanes over atoms
+        double s = 0.0;
+        for (int kk = lane; kk < R; kk += 32) s = fma(Wt[(size_t)warp * R + kk], h_s[kk], s);
+        s = warp_sum(s);
+        if (lane == 0) misc[16 + warp] = s;
+      }
+    }
+    __syncthreads();
+    // (R) ratio + cost terms for the CTA's rows (threads 0..127) and the tail rows (threads 128..128+E)
+    if (warp < 5) {
+      double cterm = 0.0;
+      const bool main_row = tid < HF_ROWS;
+      const bool tail_row = tail_rank && tid >= HF_ROWS && tid < HF_ROWS + E;
+      if (main_row || tail_row) {
+        double lam = 0.0;
+        if (main_row) {
+#pragma unroll
+          for (int q = 0; q < HF_KG; ++q) lam += lam_part[q * HF_ROWS + tid];
+        } else {
+          lam = misc[16 + tid - HF_ROWS];
+        }
+        lam = fmax(lam, flr);
+        const double v = v_s[tid];
+        const double rr = v / lam;
+        if (sc.cost_check && it >= 1) cterm = v * log(rr) - v + lam;   // sparse_nmf.m:250
+        r_s[tid] = rr;
+        r_sw[tid ^ 1] = rr;
+      }
+      cterm = warp_sum(cterm);
+      if (lane == 0) misc[warp] = cterm;
+    }
+    __syncthreads();
+    // (B) g partial over this CTA's rows: lane <-> atom kB, half-warps split the rows, pairs of rows per step
+    double* xb = xch + (size_t)buf * L.XN;
+    if (kb * 16 < R) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (kB < R) {
+        const int sw = kB & 15;  // == kl
+        const double2* wp = reinterpret_cast<const double2*>(Ws + (size_t)kB * HF_ROWS + fh * 64);
+        // element f lives at f ^ sw; the aligned pair {f, f+1} (f even) is the pair ((f ^ sw) >> 1), stored in swapped
+        // order when sw is odd -> read the ratio from the pair-swapped copy in that case
+        const double2* rp = reinterpret_cast<const double2*>(((sw & 1) ? r_sw : r_s) + fh * 64);
+        const int ps = sw >> 1;
+#pragma unroll 4
+        for (int i = 0; i < 32; i += 2) {
+          const double2 w0 = wp[i ^ ps], q0 = rp[i];
+          const double2 w1 = wp[(i + 1) ^ ps], q1 = rp[i + 1];
+          a0 = fma(w0.x, q0.x, a0);
+          a1 = fma(w0.y, q0.y, a1);
+          a2 = fma(w1.x, q1.x, a2);
+          a3 = fma(w1.y, q1.y, a3);
+        }
+      }
+      double g = (a0 + a1) + (a2 + a3);
+      g += __shfl_xor_sync(0xffffffffu, g, 16);
+      if (fh == 0 && kB < R) {
+        if (tail_rank)
+          for (int e = 0; e < E; ++e) g = fma(Wt[(size_t)e * R + kB], r_s[HF_ROWS + e], g);
+        xb[kB] = g;
+      }
+    } else if (warp == HF_WARPS - 1) {
+      double s = 0.0;  // sum of h for the sparsity term of the cost (identical order on every CTA)
+      for (int kk = lane; kk < R; kk += 32) s += h_s[kk];
+      s = warp_sum(s);
+      if (lane == 0) misc[8] = s;
+    } else if (warp == HF_WARPS - 2) {
+      if (lane == 0) xb[R] = ((misc[0] + misc[1]) + (misc[2] + misc[3])) + misc[4];
+    }
+    cluster.sync();
+    // (C) combine the 4 CTAs in rank order, convergence test, h update
+    double gk = 0.0;
+    if (tid < R)
+      for (int c = 0; c < HF_CL; ++c) gk += cluster.map_shared_rank(xb, c)[tid];
+    bool stop = false;
+    if (sc.cost_check && it >= 1) {
+      double div = 0.0;
+      for (int c = 0; c < HF_CL; ++c) div += cluster.map_shared_rank(xb, c)[R];
+      cost = div + sc.sparsity * misc[8];                                // :261
+      if (it > 1 && sc.conv_eps > 0.0) {
+        const double e = fabs(cost - last_cost) / last_cost;             // :274
+        if (e < sc.conv_eps) stop = true;
+      }
+      last_cost = cost;
+    }
+    if (it >= sc.max_iter) stop = true;
+    if (stop) break;
+    if (tid < R) h_s[tid] = h_s[tid] * gk / dph_s[tid];                   // :195
+    __syncthreads();
+    buf ^= 1;
+    ++it;
+  }
+
+  // ---- outputs ----
+  __syncthreads();
+  if (tid < R) {
+    if (rank == 0) st.A[(size_t)slot * R + tid] = h_s[tid];
+    dph_s[tid] = h_s[tid] * wn_s[tid];   // activations for the un-normalised basis (bnmf_sep_event_RT_IS16.m:174,197)
+  }
+  if (rank == 0 && tid == 0) {
+    st.h_iters[slot] = it;
+    st.h_cost[slot] = cost;
+  }
+  __syncthreads();
+  for (int part = 0; part < 2; ++part) {
+    const int k_lo = part == 0 ? 0 : R1, k_hi = part == 0 ? R1 : R;
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = k_lo + kg; k < k_hi; k += HF_KG) {
+      const double hk = dph_s[k];
+      const double* w0 = Ws + (size_t)k * HF_ROWS + rh * 64 + (lane ^ (k & 15));
+      a0 = fma(w0[0], hk, a0);
+      a1 = fma(w0[32], hk, a1);
+    }
+    lam_part[kg * HF_ROWS + rh * 64 + lane] = a0;
+    lam_part[kg * HF_ROWS + rh * 64 + lane + 32] = a1;
+    if (tail_rank && warp < E) {
+      double s = 0.0;
+      for (int kk = k_lo + lane; kk < k_hi; kk += 32) s = fma(Wt[(size_t)warp * R + kk], dph_s[kk], s);
+      s = warp_sum(s);
+      if (lane == 0) misc[16 + warp] = s;
+    }
+    __syncthreads();
+    double* dst = (part == 0 ? st.Xhat : st.Dhat) + (size_t)slot * LDF;
+    if (tid < HF_ROWS) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < HF_KG; ++q) s += lam_part[q * HF_ROWS + tid];
+      dst[f0 + tid] = s;
+    } else if (tail_rank && tid < HF_ROWS + E) {
+      dst[HF_CL * HF_ROWS + tid - HF_ROWS] = misc[16 + tid - HF_ROWS];
+    }
+    __syncthreads();
+  }
+  cluster.sync();  // nobody may exit while a peer can still read its exchange buffers
+}
+
+bool hsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
+  const int E = d.F - HF_CL * HF_ROWS;
+  if (E < 0 || E > 8) return false;
+  if (d.R > HF_THREADS || (d.R + 15) / 16 > HF_WARPS - 2) return false;  // two warps are kept for the cost / sum(h) roles
+  return (int)hf_layout(d.F, d.R).bytes <= ctx->max_smem_optin;
+}
+
+void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                        const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
+  const HfLayout L = hf_layout(d.F, d.R);
+  SN_CUDA(cudaFuncSetAttribute(hsolve_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+  hsolve_fast_kernel<<<dim3(HF_CL * n_active), dim3(HF_THREADS), L.bytes, ctx->stream>>>(d, sc, st, fr, h_init, g_step);
+  count_launch(ctx);
+  check_launch(ctx, "hsolve_fast_kernel");
+}
+
+// =====================================================================================================
+// W-solve, fast path
+// =====================================================================================================
+constexpr int WF_WARPS = 17;            // 16 tile warps + 1 warp for the leftover tile
+constexpr int WF_THREADS = WF_WARPS * 32;
+constexpr int WF_CL = 4;
+constexpr int WF_TPC = 16;              // full tiles per CTA
+
+template <int KT>
+struct WfLayout {
+  static constexpr int KMAX = KT * 8;
+  static constexpr int XN = 3 * KMAX + 8;
+  int NP, HSd, VS, VROWS;
+  size_t off_H, off_V, off_red, off_xch, off_hs, off_wn, off_tot, off_tab, off_scratch, bytes;
+  __host__ __device__ WfLayout(int m_a) {
+    NP = (m_a + 15) / 16 * 16;
+    HSd = NP + ((2 - NP % 8) + 8) % 8;          // == 2 (mod 8): conflict-free fragment loads in both GEMMs
+    VROWS = (WF_TPC + 1) * 8;                   // 136 local rows (leftover tile included)
+    VS = VROWS + 1;                             // odd stride: conflict-free (t, row) fragment reads
+    size_t o = 0;
+    off_H = o;       o += (size_t)KMAX * HSd;
+    off_V = o;       o += (size_t)NP * VS;
+    off_red = o;     o += (size_t)2 * WF_WARPS * KMAX;
+    off_xch = o;     o += (size_t)2 * XN;
+    off_hs = o;      o += KMAX;
+    off_wn = o;      o += KMAX;
+    off_tot = o;     o += 2 * KMAX;
+    o = (o + 1) & ~(size_t)1;
+    off_tab = o;     o += 256;
+    off_scratch = o; o += 64;
+    bytes = o * sizeof(double);
+  }
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double rows8_sum_f(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+template <int KT>
+__global__ void __cluster_dims__(WF_CL, 1, 1) __launch_bounds__(WF_THREADS, 1)
+wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr, int has_trace, int g_step,
+                   const double2* __restrict__ log_tab) {
+  using LT = WfLayout<KT>;
+  constexpr int KMAX = LT::KMAX;
+  constexpr int XN = LT::XN;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int slot = blockIdx.x / WF_CL;
+  const int l = g_step + 1 - st.l_offset[slot];
+  if (l < 1 || l > st.n_hops[slot]) return;
+  if (!st.do_update[slot]) return;  // uniform over the cluster
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int F = d.F, LDF = d.LDF, R_a = d.R_a, R_d = d.R_d, n = d.m_a;
+  const double flr = sc.flr;
+  const LT L(n);
+  const int HSd = L.HSd, NP = L.NP, VS = L.VS;
+
+  extern __shared__ __align__(16) double smem[];
+  double* Hs = smem + L.off_H;
+  double* Vs = smem + L.off_V;        // [NP][VS]: V slice of this CTA, pad = floor
+  double* red = smem + L.off_red;     // [2][WF_WARPS][KMAX]
+  double* xch = smem + L.off_xch;     // [2][XN]
+  double* hs_s = smem + L.off_hs;
+  double* wn_s = smem + L.off_wn;
+  double* tot = smem + L.off_tot;     // [2][KMAX]
+  double2* tab = reinterpret_cast<double2*>(smem + L.off_tab);
+  double* scratch = smem + L.off_scratch;
+
+  const int Ru = st.n_up[slot];
+  const int kt = (Ru + 7) / 8;
+  const int* __restrict__ idx_up = st.idx_up + (size_t)slot * R_a;
+  const int* __restrict__ idx_rem = st.idx_rem + (size_t)slot * R_a;
+  const int sel = st.bd_sel[slot];
+  const double* __restrict__ Bcur = st.Bd[sel] + (size_t)slot * R_d * LDF;
+  double* __restrict__ Bnext = st.Bd[sel ^ 1] + (size_t)slot * R_d * LDF;
+  const double* __restrict__ Vg = st.lam_blk + (size_t)slot * n * LDF;
+  const double* __restrict__ Adb = st.Ad_blk + (size_t)slot * n * R_a;
+
+  // tiles: rank r owns full tiles [16r, 16r+16); the leftover rows (F % 8) form one more tile on the last rank
+  const int NFT = F / 8;
+  const int nleft = F - NFT * 8;
+  const int row0 = rank * WF_TPC * 8;                 // first global row of this CTA's slice
+  int tile_local = warp;                               // local tile index 0..16
+  bool tile_valid;
+  if (warp < WF_TPC) tile_valid = (rank * WF_TPC + warp) < NFT;
+  else tile_valid = (nleft > 0) && (rank == WF_CL - 1);
+  int frow = row0 + tile_local * 8 + g;                // global row of this lane's fragment row
+  if (warp == WF_TPC) frow = NFT * 8 + g;
+  const bool row_valid = tile_valid && frow < F;
+  // local row index inside Vs: tiles 0..15 -> rows 0..127, leftover tile -> rows 128..135
+  const int vrow = tile_local * 8 + g;
+
+  // ---- stage the log table, V slice (v = max(v, flr), pad = flr), W fragments ----
+  if (tid < 128) tab[tid] = log_tab[tid];
+  for (int i = tid; i < NP * L.VROWS; i += WF_THREADS) {
+    const int t = i / L.VROWS, r = i - t * L.VROWS;
+    int fr_ = row0 + r;
+    bool ok = (r < WF_TPC * 8) ? (fr_ < NFT * 8) : (rank == WF_CL - 1 && (fr_ = NFT * 8 + (r - WF_TPC * 8)) < F);
+    double x = flr;
+    if (ok && t < n) x = fmax(Vg[(size_t)t * LDF + fr_], flr);                // sparse_nmf.m:169
+    Vs[(size_t)t * VS + r] = x;
+  }
+  double w[KT][2], gacc[KT][2];
+#pragma unroll
+  for (int j = 0; j < KT; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = 8 * j + 2 * tg + e;
+      double x = 0.0;
+      if (row_valid && k < Ru) x = Bcur[(size_t)idx_up[k] * LDF + frow];
+      w[j][e] = x;
+      gacc[j][e] = 0.0;
+    }
+
+  // per-warp partial of a per-column quantity -> red[which][warp][k]
+  auto warp_partial = [&](int which, auto&& f) {
+    double* rw = red + ((size_t)which * WF_WARPS + warp) * KMAX;
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double s = rows8_sum_f(f(j, e));
+        if (g == 0) rw[8 * j + 2 * tg + e] = s;
+      }
+  };
+  // CTA partial (fixed warp order) -> exchange buffer; cluster barrier; totals in rank order -> tot[which][k]
+  auto cluster_combine = [&](int nwhich, int xbuf, double extra, double* extra_out) {
+    __syncthreads();
+    double* xb = xch + (size_t)xbuf * XN;
+    for (int i = tid; i < nwhich * KMAX; i += WF_THREADS) {
+      const int which = i / KMAX, k = i - which * KMAX;
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < WF_WARPS; ++ww) s += red[((size_t)which * WF_WARPS + ww) * KMAX + k];
+      xb[i] = s;
+    }
+    if (tid == 0) xb[3 * KMAX] = extra;
+    cluster.sync();
+    for (int i = tid; i < nwhich * KMAX; i += WF_THREADS) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < WF_CL; ++c) s += cluster.map_shared_rank(xb, c)[i];
+      tot[i] = s;
+    }
+    if (extra_out) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < WF_CL; ++c) s += cluster.map_shared_rank(xb, c)[3 * KMAX];
+      *extra_out = s;
+    }
+    __syncthreads();
+  };
+
+  // column norms of init_w (sparse_nmf.m:158)
+  warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
+  cluster_combine(1, 1, 0.0, nullptr);
+  if (tid < KMAX) wn_s[tid] = (tid < Ru) ? sqrt(tot[tid]) : 1.0;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < KT; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) w[j][e] = w[j][e] / wn_s[8 * j + 2 * tg + e];   // :159
+  // H = init_h .* wn (:160), zero padded; row sums (constant over the solve)
+  for (int i = tid; i < KMAX * NP; i += WF_THREADS) {
+    const int k = i / NP, t = i - k * NP;
+    double x = 0.0;
+    if (k < Ru && t < n) x = Adb[(size_t)t * R_a + idx_up[k]] * wn_s[k];
+    Hs[(size_t)k * HSd + t] = x;
+  }
+  __syncthreads();
+  if (tid < KMAX) {
+    double s = 0.0;
+    for (int t = 0; t < n; ++t) s += Hs[(size_t)tid * HSd + t];
+    hs_s[tid] = s;
+  }
+  __syncthreads();
+  double hsum_all = 0.0;
+  for (int k = 0; k < Ru; ++k) hsum_all += hs_s[k];
+
+  // ---- multiplicative updates ----
+  int it = 0;
+  double last_cost = INFINITY, cost = 0.0;
+  const int ngroups = NP / 16;
+  const double* vbase = Vs + vrow;
+  for (;;) {
+    double cacc = 0.0;
+    const bool want_cost = sc.cost_check && it >= 1;
+    for (int tgp = 0; tgp < ngroups; ++tgp) {
+      const int n0 = tgp * 16;
+      // GEMM 1: lambda tile = W * H for 16 history columns (even columns -> c0, odd -> c1)
+      double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < KT; ++j)
+        if (j < kt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double2 b = *reinterpret_cast<const double2*>(Hs + (size_t)(8 * j + 2 * tg + e) * HSd + n0 + 2 * g);
+            dmma884(c0[0], c0[1], w[j][e], b.x);
+            dmma884(c1[0], c1[1], w[j][e], b.y);
+          }
+        }
+      // ratio v./lambda and cost terms; this lane holds history columns n0+4tg+q, q=0..3
+      double rt[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double lam = fmax((q & 1) ? c1[q >> 1] : c0[q >> 1], flr);                 // :243
+        const double v = vbase[(size_t)(n0 + 4 * tg + q) * VS];
+        const double r = v * fast_rcp(lam);
+        if (want_cost) cacc += fma(v, fast_log(r, tab), lam - v);                         // :250
+        rt[q] = r;
+      }
+      // GEMM 2: G tile += (v./lambda) * H'
+#pragma unroll
+      for (int j = 0; j < KT; j += 2)
+        if (j < kt) {
+          const double* hp = Hs + (size_t)(8 * j + g) * HSd + n0 + 4 * tg;
+          const double2 a01 = *reinterpret_cast<const double2*>(hp);
+          const double2 a23 = *reinterpret_cast<const double2*>(hp + 2);
+          if (j + 1 < KT && j + 1 < kt) {
+            const double2 b01 = *reinterpret_cast<const double2*>(hp + 8 * HSd);
+            const double2 b23 = *reinterpret_cast<const double2*>(hp + 8 * HSd + 2);
+            dmma884(gacc[j][0], gacc[j][1], rt[0], a01.x);
+            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[0], b01.x);
+            dmma884(gacc[j][0], gacc[j][1], rt[1], a01.y);
+            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[1], b01.y);
+            dmma884(gacc[j][0], gacc[j][1], rt[2], a23.x);
+            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[2], b23.x);
+            dmma884(gacc[j][0], gacc[j][1], rt[3], a23.y);
+            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[3], b23.y);
+          } else {
+            dmma884(gacc[j][0], gacc[j][1], rt[0], a01.x);
+            dmma884(gacc[j][0], gacc[j][1], rt[1], a01.y);
+            dmma884(gacc[j][0], gacc[j][1], rt[2], a23.x);
+            dmma884(gacc[j][0], gacc[j][1], rt[3], a23.y);
+          }
+        }
+    }
+    // column reductions: cw_k = sum_f w, s_k = sum_f G.*w                               :215-221
+    warp_partial(0, [&](int j, int e) { return w[j][e]; });
+    warp_partial(1, [&](int j, int e) { return gacc[j][e] * w[j][e]; });
+    const double cpart = block_sum(cacc, scratch);
+    double div = 0.0;
+    cluster_combine(2, 0, cpart, &div);
+    bool stop = false;
+    if (want_cost) {
+      cost = div + sc.sparsity * hsum_all;                                               // :261
+      if (it > 1 && sc.conv_eps > 0.0) {
+        const double e = fabs(cost - last_cost) / last_cost;
+        if (e < sc.conv_eps) stop = true;
+      }
+      last_cost = cost;
+    }
+    if (it >= sc.max_iter) stop = true;
+    if (stop) break;
+    // W update                                                                          :215-222
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 8 * j + 2 * tg + e;
+        const double wv = w[j][e];
+        const double hs = hs_s[k];
+        const double dpw = fmax(hs + tot[KMAX + k] * wv, flr);
+        const double dmw = gacc[j][e] + (hs * tot[k]) * wv;
+        w[j][e] = (k < Ru) ? wv * dmw / dpw : 0.0;
+        gacc[j][e] = 0.0;
+      }
+    // column normalisation                                                              :242
+    warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
+    cluster_combine(1, 1, 0.0, nullptr);
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 8 * j + 2 * tg + e;
+        if (k < Ru) w[j][e] = w[j][e] / sqrt(tot[k]);
+      }
+    ++it;
+  }
+
+  // ---- B_DFT_d = [B_rem, B_new, B_fix]  (bnmf_sep_event_RT_IS16.m:336) into the other buffer ----
+  const int n_rem = R_a - Ru;
+#pragma unroll
+  for (int j = 0; j < KT; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = 8 * j + 2 * tg + e;
+      if (row_valid && k < Ru) Bnext[(size_t)(n_rem + k) * LDF + frow] = w[j][e];
+    }
+  {
+    const double* __restrict__ Bfix = st.Bd_fix + (size_t)slot * st.bdfix_stride;
+    const int rb = F / WF_CL, rr = F % WF_CL;
+    const int rows = rb + (rank < rr ? 1 : 0);
+    const int r0 = rank * rb + (rank < rr ? rank : rr);
+    const int ncopy = n_rem + (R_d - R_a);
+    for (int i = tid; i < ncopy * rows; i += WF_THREADS) {
+      const int cidx = i / rows, f = r0 + i % rows;
+      if (cidx < n_rem) Bnext[(size_t)cidx * LDF + f] = Bcur[(size_t)idx_rem[cidx] * LDF + f];
+      else {
+        const int k = R_a + (cidx - n_rem);
+        Bnext[(size_t)k * LDF + f] = Bfix[(size_t)k * LDF + f];
+      }
+    }
+  }
+  if (rank == 0 && tid == 0) {
+    st.w_iters[slot] = it;
+    atomicAdd(&st.stats[2], (unsigned long long)it);
+    if (has_trace) tr.info[(st.frame_base[slot] + g_step) * 4 + 3] = it;
+  }
+  cluster.sync();  // peers may still be reading this CTA's exchange buffers
+  if (rank == 0 && tid == 0) st.bd_sel[slot] = sel ^ 1;
+}
+
+bool wsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
+  if (d.R_a > 64 || d.R_a < 1) return false;
+  if ((d.F + 7) / 8 > WF_CL * WF_TPC + 1 || d.F / 8 > WF_CL * WF_TPC) return false;
+  const size_t bytes = d.R_a <= 56 ? WfLayout<7>(d.m_a).bytes : WfLayout<8>(d.m_a).bytes;
+  return (int)bytes <= ctx->max_smem_optin;
+}
+
+void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                        const TraceArrays* tr, int n_active, int g_step) {
+  const double2* tab = log_table(ctx);
+  TraceArrays t{};
+  if (tr) t = *tr;
+  if (d.R_a <= 56) {
+    const size_t smem = WfLayout<7>(d.m_a).bytes;
+    SN_CUDA(cudaFuncSetAttribute(wsolve_fast_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wsolve_fast_kernel<7><<<dim3(WF_CL * n_active), dim3(WF_THREADS), smem, ctx->stream>>>(d, sc, st, t, tr ? 1 : 0,
+                                                                                            g_step, tab);
+  } else {
+    const size_t smem = WfLayout<8>(d.m_a).bytes;
+    SN_CUDA(cudaFuncSetAttribute(wsolve_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wsolve_fast_kernel<8><<<dim3(WF_CL * n_active), dim3(WF_THREADS), smem, ctx->stream>>>(d, sc, st, t, tr ? 1 : 0,
+                                                                                            g_step, tab);
+  }
+  count_launch(ctx);
+  check_launch(ctx, "wsolve_fast_kernel");
+}
+
+}  // namespace snmfnat

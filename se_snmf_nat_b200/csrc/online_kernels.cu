@@ -11,6 +11,7 @@
 //                    (mma.sync m8n8k4.f64) with W and R*H' tiles held in registers.
 #include <cooperative_groups.h>
 #include <cmath>
+#include <cstdlib>
 #include "online.cuh"
 
 namespace cg = cooperative_groups;
@@ -262,9 +263,22 @@ hsolve_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, cons
   cluster.sync();  // nobody may exit while a peer can still read its exchange buffers
 }
 
+bool force_generic() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SNMFNAT_FORCE_GENERIC");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
   if (n_active <= 0) return;
+  if (!force_generic() && hsolve_fast_supported(ctx, d)) {
+    launch_hsolve_fast(ctx, d, sc, st, fr, h_init, n_active, g_step);
+    return;
+  }
   const HsLayout L = hs_layout(d.F, d.R);
   SN_REQUIRE(d.R <= HS_THREADS, SNMFNAT_EUNSUPPORTED, "H-solve kernel supports R_x+R_d <= %d (got %d)", HS_THREADS, d.R);
   SN_REQUIRE((int)L.bytes <= ctx->max_smem_optin, SNMFNAT_EUNSUPPORTED,
@@ -915,6 +929,10 @@ wsolve_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr, int 
 void launch_wsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const TraceArrays* tr, int n_active, int g_step) {
   if (n_active <= 0 || !sc.adapt_train_N) return;
+  if (!force_generic() && wsolve_fast_supported(ctx, d)) {
+    launch_wsolve_fast(ctx, d, sc, st, tr, n_active, g_step);
+    return;
+  }
   SN_REQUIRE(d.R_a <= WS_KMAX, SNMFNAT_EUNSUPPORTED, "W-solve kernel supports R_a <= %d (got %d)", WS_KMAX, d.R_a);
   SN_REQUIRE(d.F / 8 <= 2 * WS_CL * WS_WARPS, SNMFNAT_EUNSUPPORTED, "W-solve kernel supports F <= %d (got %d)",
              16 * WS_CL * WS_WARPS + 7, d.F);
