@@ -1,7 +1,7 @@
 // Second-generation per-hop MU kernels for the shipped geometry (fftlength 1024 -> F = 513 rows).
 //
 // hsolve_fast_kernel : 4-CTA cluster per stream, 16 warps per CTA.  Each CTA keeps 128 rows of W = [B_x B_d] in
-//   shared memory with an XOR swizzle, element (k,f) at k*128 + (f ^ (k & 15)), so that BOTH directions of the
+//   shared memory with an XOR swizzle, element (k,f) at k*128 + (f ^ 2*(k & 7)) (row pairs permuted), so that BOTH directions of the
 //   mat-vec pair are bank-conflict free without any cross-lane reduction:
 //     lambda = W h   : lanes <-> rows   (one column k per step, h_k broadcast)
 //     g = W'(v./lambda): lanes <-> atoms (one row pair per step, ratio broadcast)
@@ -88,7 +88,7 @@ constexpr int HF_KG = 8;       // k groups in the lambda pass
 
 struct HfLayout {
   int E, XN;
-  size_t off_W, off_Wt, off_v, off_r, off_rsw, off_lam, off_h, off_dph, off_wn, off_xch, off_misc, bytes;
+  size_t off_W, off_Wt, off_v, off_r, off_lam, off_h, off_dph, off_wn, off_xch, off_misc, bytes;
 };
 __host__ __device__ inline HfLayout hf_layout(int F, int R) {
   HfLayout L;
@@ -100,7 +100,6 @@ __host__ __device__ inline HfLayout hf_layout(int F, int R) {
   o = (o + 1) & ~(size_t)1;
   L.off_v = o;    o += HF_ROWS + 8;
   L.off_r = o;    o += HF_ROWS + 8;
-  L.off_rsw = o;  o += HF_ROWS + 8;
   L.off_lam = o;  o += (size_t)HF_KG * HF_ROWS;
   L.off_h = o;    o += R;
   L.off_dph = o;  o += R;
@@ -128,12 +127,11 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
   const bool tail_rank = (rank == HF_CL - 1) && E > 0;
   const int f0 = rank * HF_ROWS;
 
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(1024) double smem[];
   double* Ws = smem + L.off_W;
   double* Wt = smem + L.off_Wt;       // [E][R] tail rows (last rank only)
   double* v_s = smem + L.off_v;       // [128 + E]
   double* r_s = smem + L.off_r;       // ratio v./lambda
-  double* r_sw = smem + L.off_rsw;    // r_sw[f] = r_s[f ^ 1]
   double* lam_part = smem + L.off_lam;
   double* h_s = smem + L.off_h;
   double* dph_s = smem + L.off_dph;
@@ -151,7 +149,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
   for (int k = warp; k < R; k += HF_WARPS) {
     const double* src = (k < R1 ? W1 + (size_t)k * LDF : W2 + (size_t)(k - R1) * LDF);
     double s1 = 0.0, s2 = 0.0;
-    const int sw = k & 15;
+    const int sw = (k & 7) << 1;
 #pragma unroll
     for (int j = 0; j < HF_ROWS / 32; ++j) {
       const int f = lane + 32 * j;
@@ -213,13 +211,12 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     // (A) lambda partials: this warp sums columns k = kg, kg+8, ... for rows rh*64 + lane + {0,32}
     {
       double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-      const double* base = Ws + rh * 64;
-      const int x0 = lane ^ kg, x1 = lane ^ (kg | 8);
+      const double* base = Ws + rh * 64 + (lane ^ (kg << 1));   // k & 7 == kg for every column of this group
       int k = kg;
       for (; k + 8 < R; k += 16) {
         const double h0 = h_s[k], h1 = h_s[k + 8];
-        const double* w0 = base + (size_t)k * HF_ROWS + x0;
-        const double* w1 = base + (size_t)(k + 8) * HF_ROWS + x1;
+        const double* w0 = base + (size_t)k * HF_ROWS;
+        const double* w1 = base + (size_t)(k + 8) * HF_ROWS;
         a0 = fma(w0[0], h0, a0);
         a1 = fma(w0[32], h0, a1);
         b0 = fma(w1[0], h1, b0);
@@ -227,7 +224,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
       }
       if (k < R) {
         const double h0 = h_s[k];
-        const double* w0 = base + (size_t)k * HF_ROWS + x0;
+        const double* w0 = base + (size_t)k * HF_ROWS;
         a0 = fma(w0[0], h0, a0);
         a1 = fma(w0[32], h0, a1);
       }
@@ -259,7 +256,6 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
         const double rr = v / lam;
         if (sc.cost_check && it >= 1) cterm = v * log(rr) - v + lam;   // sparse_nmf.m:250
         r_s[tid] = rr;
-        r_sw[tid ^ 1] = rr;
       }
       cterm = warp_sum(cterm);
       if (lane == 0) misc[warp] = cterm;
@@ -270,16 +266,16 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     if (kb * 16 < R) {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       if (kB < R) {
-        const int sw = kB & 15;  // == kl
-        const double2* wp = reinterpret_cast<const double2*>(Ws + (size_t)kB * HF_ROWS + fh * 64);
-        // element f lives at f ^ sw; the aligned pair {f, f+1} (f even) is the pair ((f ^ sw) >> 1), stored in swapped
-        // order when sw is odd -> read the ratio from the pair-swapped copy in that case
-        const double2* rp = reinterpret_cast<const double2*>(((sw & 1) ? r_sw : r_s) + fh * 64);
-        const int ps = sw >> 1;
-#pragma unroll 4
+        // row pair i of atom kB lives at pair slot i ^ (kB & 7); the row base is 512-byte aligned, so the byte address
+        // of that slot is (base ^ ((kB & 7) << 4)) ^ (i << 4): one LOP3 per 16-byte load
+        const unsigned wx = (unsigned)__cvta_generic_to_shared(Ws + (size_t)kB * HF_ROWS + fh * 64) ^ ((unsigned)(kB & 7) << 4);
+        const double2* rp = reinterpret_cast<const double2*>(r_s + fh * 64);
+#pragma unroll 8
         for (int i = 0; i < 32; i += 2) {
-          const double2 w0 = wp[i ^ ps], q0 = rp[i];
-          const double2 w1 = wp[(i + 1) ^ ps], q1 = rp[i + 1];
+          double2 w0, w1;
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w0.x), "=d"(w0.y) : "r"(wx ^ ((unsigned)i << 4)));
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w1.x), "=d"(w1.y) : "r"(wx ^ ((unsigned)(i + 1) << 4)));
+          const double2 q0 = rp[i], q1 = rp[i + 1];
           a0 = fma(w0.x, q0.x, a0);
           a1 = fma(w0.y, q0.y, a1);
           a2 = fma(w1.x, q1.x, a2);
@@ -341,7 +337,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     double a0 = 0.0, a1 = 0.0;
     for (int k = k_lo + kg; k < k_hi; k += HF_KG) {
       const double hk = dph_s[k];
-      const double* w0 = Ws + (size_t)k * HF_ROWS + rh * 64 + (lane ^ (k & 15));
+      const double* w0 = Ws + (size_t)k * HF_ROWS + rh * 64 + (lane ^ ((k & 7) << 1));
       a0 = fma(w0[0], hk, a0);
       a1 = fma(w0[32], hk, a1);
     }
@@ -488,14 +484,19 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 
   // ---- stage the log table, V slice (v = max(v, flr), pad = flr), W fragments ----
   if (tid < 128) tab[tid] = log_tab[tid];
-  for (int i = tid; i < NP * L.VROWS; i += WF_THREADS) {
-    const int t = i / L.VROWS, r = i - t * L.VROWS;
-    int fr_ = row0 + r;
-    bool ok = (r < WF_TPC * 8) ? (fr_ < NFT * 8) : (rank == WF_CL - 1 && (fr_ = NFT * 8 + (r - WF_TPC * 8)) < F);
-    double x = flr;
-    if (ok && t < n) x = fmax(Vg[(size_t)t * LDF + fr_], flr);                // sparse_nmf.m:169
-    Vs[(size_t)t * VS + r] = x;
-  }
+  for (int t = warp; t < NP; t += WF_WARPS)
+    for (int r = lane; r < L.VROWS; r += 32) {
+      int fr_ = row0 + r;
+      bool ok;
+      if (r < WF_TPC * 8) ok = fr_ < NFT * 8;
+      else {
+        fr_ = NFT * 8 + (r - WF_TPC * 8);
+        ok = (rank == WF_CL - 1) && fr_ < F;
+      }
+      double x = flr;
+      if (ok && t < n) x = fmax(Vg[(size_t)t * LDF + fr_], flr);                // sparse_nmf.m:169
+      Vs[(size_t)t * VS + r] = x;
+    }
   double w[KT][2], gacc[KT][2];
 #pragma unroll
   for (int j = 0; j < KT; ++j)
@@ -520,7 +521,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       }
   };
   // CTA partial (fixed warp order) -> exchange buffer; cluster barrier; totals in rank order -> tot[which][k]
-  auto cluster_combine = [&](int nwhich, int xbuf, double extra, double* extra_out) {
+  auto cluster_combine = [&](int nwhich, int xbuf, bool with_cost, double* extra_out) {
     __syncthreads();
     double* xb = xch + (size_t)xbuf * XN;
     for (int i = tid; i < nwhich * KMAX; i += WF_THREADS) {
@@ -530,7 +531,12 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       for (int ww = 0; ww < WF_WARPS; ++ww) s += red[((size_t)which * WF_WARPS + ww) * KMAX + k];
       xb[i] = s;
     }
-    if (tid == 0) xb[3 * KMAX] = extra;
+    if (with_cost && tid == WF_THREADS - 1) {  // per-warp cost partials, fixed order
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < WF_WARPS; ++ww) s += scratch[ww];
+      xb[3 * KMAX] = s;
+    }
     cluster.sync();
     for (int i = tid; i < nwhich * KMAX; i += WF_THREADS) {
       double s = 0.0;
@@ -549,7 +555,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 
   // column norms of init_w (sparse_nmf.m:158)
   warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
-  cluster_combine(1, 1, 0.0, nullptr);
+  cluster_combine(1, 1, false, nullptr);
   if (tid < KMAX) wn_s[tid] = (tid < Ru) ? sqrt(tot[tid]) : 1.0;
   __syncthreads();
 #pragma unroll
@@ -557,11 +563,15 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 #pragma unroll
     for (int e = 0; e < 2; ++e) w[j][e] = w[j][e] / wn_s[8 * j + 2 * tg + e];   // :159
   // H = init_h .* wn (:160), zero padded; row sums (constant over the solve)
-  for (int i = tid; i < KMAX * NP; i += WF_THREADS) {
-    const int k = i / NP, t = i - k * NP;
-    double x = 0.0;
-    if (k < Ru && t < n) x = Adb[(size_t)t * R_a + idx_up[k]] * wn_s[k];
-    Hs[(size_t)k * HSd + t] = x;
+  for (int k = warp; k < KMAX; k += WF_WARPS) {
+    const bool kv = k < Ru;
+    const int src = kv ? idx_up[k] : 0;
+    const double wn = wn_s[k];
+    for (int t = lane; t < NP; t += 32) {
+      double x = 0.0;
+      if (kv && t < n) x = Adb[(size_t)t * R_a + src] * wn;
+      Hs[(size_t)k * HSd + t] = x;
+    }
   }
   __syncthreads();
   if (tid < KMAX) {
@@ -634,9 +644,10 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
     // column reductions: cw_k = sum_f w, s_k = sum_f G.*w                               :215-221
     warp_partial(0, [&](int j, int e) { return w[j][e]; });
     warp_partial(1, [&](int j, int e) { return gacc[j][e] * w[j][e]; });
-    const double cpart = block_sum(cacc, scratch);
+    cacc = warp_sum(cacc);
+    if (lane == 0) scratch[warp] = cacc;
     double div = 0.0;
-    cluster_combine(2, 0, cpart, &div);
+    cluster_combine(2, 0, true, &div);
     bool stop = false;
     if (want_cost) {
       cost = div + sc.sparsity * hsum_all;                                               // :261
@@ -663,7 +674,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       }
     // column normalisation                                                              :242
     warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
-    cluster_combine(1, 1, 0.0, nullptr);
+    cluster_combine(1, 1, false, nullptr);
 #pragma unroll
     for (int j = 0; j < KT; ++j)
 #pragma unroll
@@ -684,18 +695,15 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       if (row_valid && k < Ru) Bnext[(size_t)(n_rem + k) * LDF + frow] = w[j][e];
     }
   {
-    const double* __restrict__ Bfix = st.Bd_fix + (size_t)slot * st.bdfix_stride;
+    // the not-updated adaptable atoms move to the front; columns >= R_a never change and are valid in both
+    // buffers since the reset (state.cu), so they are not copied
     const int rb = F / WF_CL, rr = F % WF_CL;
     const int rows = rb + (rank < rr ? 1 : 0);
     const int r0 = rank * rb + (rank < rr ? rank : rr);
-    const int ncopy = n_rem + (R_d - R_a);
-    for (int i = tid; i < ncopy * rows; i += WF_THREADS) {
-      const int cidx = i / rows, f = r0 + i % rows;
-      if (cidx < n_rem) Bnext[(size_t)cidx * LDF + f] = Bcur[(size_t)idx_rem[cidx] * LDF + f];
-      else {
-        const int k = R_a + (cidx - n_rem);
-        Bnext[(size_t)k * LDF + f] = Bfix[(size_t)k * LDF + f];
-      }
+    for (int c = warp; c < n_rem; c += WF_WARPS) {
+      const double* __restrict__ src = Bcur + (size_t)idx_rem[c] * LDF + r0;
+      double* __restrict__ dst = Bnext + (size_t)c * LDF + r0;
+      for (int f = lane; f < rows; f += 32) dst[f] = src[f];
     }
   }
   if (rank == 0 && tid == 0) {

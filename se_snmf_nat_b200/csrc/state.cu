@@ -121,8 +121,8 @@ void SlotBuffers::reset(snmfnat_ctx* ctx) {
   int blocks = (int)((per * S + 255) / 256);
   if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
   broadcast_kernel<<<blocks, 256, 0, st>>>(Bd_fix.p, Bd0.p, per, S);
-  count_launch(ctx);
-  Bd1.zero(st);
+  broadcast_kernel<<<blocks, 256, 0, st>>>(Bd_fix.p, Bd1.p, per, S);  // columns >= R_a must be valid in both buffers
+  count_launch(ctx, 2);
   if (Ad_blk.n) SN_CUDA(cudaMemcpyAsync(Ad_blk.p, Ad_init.p, Ad_blk.n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   check_launch(ctx, "state reset");
 }
