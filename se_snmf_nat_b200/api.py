@@ -295,3 +295,274 @@ def filewise_run_IS16(path_in: str, path_denoise: str, p: dict, B_DFT_x, B_DFT_d
         w.setframerate(int(p.get("fs", 16000)))
         w.writeframes(out.astype("<i2").tobytes())
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# L1 numeric functions (same names / argument meaning as the reference's src/*.m)
+# ----------------------------------------------------------------------------------------------------------------
+def _nmf_opts(p: dict, n: int, r: int, *, sparsity_key="sparsity", conv_key="conv_eps"):
+    """Optional fields of p with the defaults of sparse_nmf.m:79-97; `cost_check` has no default there (:260)."""
+    if "cost_check" not in p:
+        raise KeyError("p.cost_check is required (sparse_nmf.m:260 reads it without a default)")
+    o = NmfOpts()
+    o.max_iter = int(p.get("max_iter", 100))
+    cf = p.get("cf", "kl")
+    if isinstance(cf, str):
+        if cf in _CF:
+            o.cf = _CF[cf]
+        else:
+            o.cf = _lib.CF_BETA
+            o.beta_div = float(p.get("beta", 1.0))
+    else:
+        o.cf = int(cf)
+    o.cost_check = int(bool(p["cost_check"]))
+    o.conv_eps = float(p.get(conv_key, 0.0))
+    o.precision = 0
+    sp = np.asarray(p.get(sparsity_key, 0.0), dtype=np.float64)
+    if sp.size == 1:
+        sp = sp.reshape(1, 1)
+    elif sp.ndim == 1 or sp.shape[1] == 1:
+        sp = sp.reshape(r, 1)
+    elif sp.shape != (r, n):
+        raise ValueError("sparsity must be scalar, r x 1 or r x n")
+    o.sparsity_rows, o.sparsity_cols = sp.shape
+    return o, _f64(sp)
+
+
+def _nmf_inits(v, p, rand):
+    m, n = v.shape
+    if "init_w" in p:
+        w0 = np.array(p["init_w"], dtype=np.float64)
+        r = w0.shape[1]
+        if "r" in p and r < int(p["r"]):                       # sparse_nmf.m:125-127
+            if rand is None:
+                raise ValueError("p.r > size(init_w,2): pass rand= to supply MATLAB's rand(m, r-ri)")
+            w0 = np.concatenate([w0, np.asarray(rand(m, int(p["r"]) - r), dtype=np.float64)], axis=1)
+            r = int(p["r"])
+    else:
+        if "r" not in p:
+            raise ValueError("Number of components or initialization must be given")   # sparse_nmf.m:118
+        if rand is None:
+            raise ValueError("no p.init_w: pass rand= to supply MATLAB's rand(m, r) (RNG stays on the host)")
+        r = int(p["r"])
+        w0 = np.asarray(rand(m, r), dtype=np.float64)
+    ih = p.get("init_h", None)
+    if ih is None:
+        if rand is None:
+            raise ValueError("no p.init_h: pass rand= to supply MATLAB's rand(r, n) (RNG stays on the host)")
+        h0 = np.asarray(rand(r, n), dtype=np.float64)
+    elif isinstance(ih, str) and ih == "ones":
+        h0 = np.ones((r, n))
+    else:
+        h0 = np.array(ih, dtype=np.float64).reshape(r, n)
+    return _f64(w0), _f64(h0), r
+
+
+def _ind(p, key, r):
+    if key not in p or p[key] is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(p[key]).ravel().astype(np.uint8))
+    if a.size != r:
+        raise ValueError(f"{key} must have r entries")
+    return a
+
+
+def _u8ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8)) if a is not None else None
+
+
+def sparse_nmf(v, p: dict, *, rand=None, device: int = 0):
+    """[w, h, objective] = sparse_nmf(v, p)     src/sparse_nmf.m:1-292.
+    `rand(m, n)` stands in for MATLAB's rand after rand('seed', p.random_seed) when p.init_w / p.init_h are absent."""
+    ctx = get_context(device)
+    v = _f64(np.atleast_2d(np.asarray(v, dtype=np.float64)) if np.ndim(v) > 1 else np.asarray(v, dtype=np.float64).reshape(-1, 1))
+    m, n = v.shape
+    w0, h0, r = _nmf_inits(v, p, rand)
+    o, sp = _nmf_opts(p, n, r)
+    wi, hi = _ind(p, "w_update_ind", r), _ind(p, "h_update_ind", r)
+    w = np.empty((m, r), order="F")
+    h = np.empty((r, n), order="F")
+    div = np.zeros(max(o.max_iter, 1))
+    cost = np.zeros(max(o.max_iter, 1))
+    its = C.c_int(0)
+    check(ctx._lib.snmfnat_sparse_nmf(ctx._h, _dptr(v), m, n, r, C.byref(o), _dptr(sp), _dptr(w0), _dptr(h0), _u8ptr(wi),
+                                      _u8ptr(hi), _dptr(w), _dptr(h), _dptr(div), _dptr(cost), C.byref(its)))
+    k = its.value
+    return w, h, {"div": div[:k], "cost": cost[:k], "iters": k}
+
+
+def snmf_mdi(v, Dm, p: dict, *, rand=None, soft=False, device: int = 0):
+    """[v_MDI, h, objective] = snmf_mdi(v, Dm, p)   src/snmf_mdi.m (binary mask) / src/snmf_mdi_Sm.m (soft=True).
+    Reads p.sparsity_mdi / p.conv_eps_mdi (both effectively required, snmf_mdi.m:93-99)."""
+    for k in ("sparsity_mdi", "conv_eps_mdi"):
+        if k not in p:
+            raise KeyError(f"p.{k} is required (the defaults at snmf_mdi.m:93-99 test the wrong field names)")
+    ctx = get_context(device)
+    v = _f64(np.asarray(v, dtype=np.float64).reshape(np.shape(v)[0], -1))
+    m, n = v.shape
+    mk = _f64(np.asarray(Dm, dtype=np.float64).reshape(m, n))
+    w0, h0, r = _nmf_inits(v, p, rand)
+    o, sp = _nmf_opts(p, n, r, sparsity_key="sparsity_mdi", conv_key="conv_eps_mdi")
+    wi, hi = _ind(p, "w_update_ind", r), _ind(p, "h_update_ind", r)
+    out = np.empty((m, n), order="F")
+    h = np.empty((r, n), order="F")
+    div = np.zeros(max(o.max_iter, 1))
+    cost = np.zeros(max(o.max_iter, 1))
+    its = C.c_int(0)
+    check(ctx._lib.snmfnat_snmf_mdi(ctx._h, _dptr(v), _dptr(mk), 1 if soft else 0, m, n, r, C.byref(o), _dptr(sp),
+                                    _dptr(w0), _dptr(h0), _u8ptr(wi), _u8ptr(hi), _dptr(out), _dptr(h), _dptr(div),
+                                    _dptr(cost), C.byref(its)))
+    k = its.value
+    return out, h, {"div": div[:k], "cost": cost[:k], "iters": k}
+
+
+def snmf_mdi_Sm(v, Sm, p: dict, **kw):
+    """src/snmf_mdi_Sm.m: the soft-mask variant."""
+    return snmf_mdi(v, Sm, p, soft=True, **kw)
+
+
+def DNMF_adapt(Y, D, B, p: dict, *, rand, device: int = 0):
+    """B_a = DNMF_adapt(Y, D, B, p)      src/DNMF_adapt.m:1-21 (needs p.R_x, p.R_d)."""
+    ctx = get_context(device)
+    Y = _f64(Y); D = _f64(D); B = _f64(B)
+    F, n = Y.shape
+    R_x, R_d = int(p["R_x"]), int(p["R_d"])
+    o, sp = _nmf_opts(p, n, R_x + R_d)
+    h0 = _f64(np.asarray(rand(R_x + R_d, n), dtype=np.float64))
+    out = np.empty((F, R_d), order="F")
+    check(ctx._lib.snmfnat_dnmf_adapt(ctx._h, _dptr(Y), _dptr(D), _dptr(B), F, n, R_x, R_d, C.byref(o), _dptr(sp),
+                                      _dptr(h0), _dptr(out)))
+    return out
+
+
+def stft_fft(s, sz, shift, fftlen, DCbin, win, preemph, *, device: int = 0):
+    """[S_mag, S_phase] = stft_fft(s, sz, shift, fftlen, DCbin, win, preemph)     src/stft_fft.m:1-37."""
+    ctx = get_context(device)
+    s = _f64(np.asarray(s, dtype=np.float64).ravel())
+    win = _f64(np.asarray(win, dtype=np.float64).ravel())
+    if win.size != sz:
+        raise ValueError("window length must equal sz")
+    half = fftlen // 2 + 1
+    nfr = s.size // shift
+    mag = np.zeros((half, nfr), order="F")
+    ph = np.zeros((half, nfr), order="F")
+    check(ctx._lib.snmfnat_stft_fft(ctx._h, _dptr(s), s.size, int(sz), int(shift), int(fftlen), int(DCbin), _dptr(win),
+                                    float(preemph), _dptr(mag), _dptr(ph)))
+    return mag, ph
+
+
+def synth_ifft_buff(TF_mag, TF_phase, sz, fftlen, win, preemph, DCbin_back, pow_, *, device: int = 0):
+    """s_buff = synth_ifft_buff(TF_mag, TF_phase, sz, fftlen, win, preemph, DCbin_back, pow)  src/synth_ifft_buff.m:1-33."""
+    ctx = get_context(device)
+    mag = np.asarray(TF_mag, dtype=np.float64)
+    if mag.ndim == 1:
+        mag = mag[:, None]
+    mag = _f64(mag)
+    ph = None
+    if TF_phase is not None:
+        ph = _f64(np.asarray(TF_phase, dtype=np.float64).reshape(mag.shape))
+    win = _f64(np.asarray(win, dtype=np.float64).ravel())
+    out = np.empty((int(sz), mag.shape[1]), order="F")
+    check(ctx._lib.snmfnat_synth_ifft_buff(ctx._h, _dptr(mag), _dptr(ph), mag.shape[0], mag.shape[1], int(sz), int(fftlen),
+                                           _dptr(win), float(preemph), int(DCbin_back), float(pow_), _dptr(out)))
+    return out
+
+
+def blk_sparse(X, D, r_blk, l, p: dict, *, device: int = 0):
+    """[Q, r_blk_out] = blk_sparse(X, D, r_blk, l, p)      src/blk_sparse.m:1-37."""
+    ctx = get_context(device)
+    X = _f64(np.asarray(X, dtype=np.float64).ravel())
+    D = _f64(np.asarray(D, dtype=np.float64).ravel())
+    rb = _f64(r_blk)
+    ps = params_struct(p)
+    if rb.shape != (X.size, ps.P_len_l):
+        raise ValueError("r_blk must be K x P_len_l")
+    Q = np.empty(X.size)
+    rout = np.empty_like(rb, order="F")
+    check(ctx._lib.snmfnat_blk_sparse(ctx._h, _dptr(X), _dptr(D), _dptr(rb), X.size, int(l), C.byref(ps), _dptr(Q),
+                                      _dptr(rout)))
+    return Q, rout
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# L2 per-hop entry: init_buff / bnmf_sep_event_RT_IS16 with a device-resident g
+# ----------------------------------------------------------------------------------------------------------------
+class StreamState:
+    """The struct g of src/init_buff.m:17-62, resident on the device.  g["B_DFT_d"], g["Ad_blk"], ... read the fields
+    (MATLAB layouts); assignment writes them back (e.g. the B_D_u.mat carry-over of src/NTF_sep_event_RT.m:28-38)."""
+
+    _SHAPES = {"B_DFT_d": ("F", "R_d"), "B_Mel_d": ("F", "R_d"), "B_DFT_x": ("F", "R_x"), "B_Mel_x": ("F", "R_x"),
+               "Ad_blk": ("R_a", "m_a"), "lambda_d_blk": ("F", "m_a"), "r_blk": ("F", "P_len_l"),
+               "lambda_dav": ("F",), "Xm_tilde": ("F",), "Ym": ("F",), "Yp": ("F",), "A": ("R",), "Q": ("F",),
+               "G": ("F",), "Xm_hat": ("F",), "Dm_hat": ("F",), "update_switch": (1,), "stats": (5,)}
+
+    def __init__(self, ctx: Context, handle, ps: Params):
+        self.ctx, self._h, self._ps = ctx, handle, ps
+        self._dims = {"F": ps.fftlength // 2 + 1, "R_x": ps.R_x, "R_d": ps.R_d, "R": ps.R_x + ps.R_d, "R_a": ps.R_a,
+                      "m_a": ps.m_a, "P_len_l": ps.P_len_l}
+
+    def _shape(self, name):
+        if name not in self._SHAPES:
+            raise KeyError(name)
+        return tuple(self._dims.get(x, x) for x in self._SHAPES[name])
+
+    def __getitem__(self, name):
+        shp = self._shape(name)
+        buf = np.empty(shp, dtype=np.float64, order="F")
+        check(self.ctx._lib.snmfnat_stream_get(self._h, name.encode(), _dptr(buf), buf.size))
+        return buf
+
+    def __setitem__(self, name, value):
+        shp = self._shape(name)
+        buf = _f64(np.asarray(value, dtype=np.float64).reshape(shp))
+        check(self.ctx._lib.snmfnat_stream_set(self._h, name.encode(), _dptr(buf), buf.size))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.snmfnat_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def init_buff(B_Mel_x, B_Mel_d, B_DFT_x, B_DFT_d, p: dict, *, Ad_blk_init, A_d_init=None, device: int = 0) -> StreamState:
+    """g = init_buff(B_Mel_x, B_Mel_d, B_DFT_x, B_DFT_d, p)   src/init_buff.m:1-62.  The two rand() draws at :37-38
+    are arguments (Ad_blk_init R_a x m_a, A_d_init R_d x 1)."""
+    ctx = get_context(device)
+    ps = params_struct(p)
+    Bmx, Bmd, Bx, Bd = _f64(B_Mel_x), _f64(B_Mel_d), _f64(B_DFT_x), _f64(B_DFT_d)
+    win_s = _f64(np.asarray(p.get("win_STFT", sqrt_hann_periodic(ps.framelength))).ravel())
+    win_i = _f64(np.asarray(p.get("win_ISTFT", sqrt_hann_periodic(ps.framelength))).ravel())
+    ad = _f64(np.asarray(Ad_blk_init, dtype=np.float64).reshape(ps.R_a, ps.m_a)) if Ad_blk_init is not None else None
+    a_d = _f64(np.asarray(A_d_init, dtype=np.float64).ravel()) if A_d_init is not None else None
+    h = C.c_void_p()
+    check(ctx._lib.snmfnat_stream_create(ctx._h, C.byref(ps), _dptr(win_s), _dptr(win_i), _dptr(Bmx), _dptr(Bmd),
+                                         Bmd.shape[0], _dptr(Bx), _dptr(Bd), Bx.shape[0], _dptr(ad), _dptr(a_d),
+                                         C.byref(h)))
+    return StreamState(ctx, h, ps)
+
+
+def bnmf_sep_event_RT_IS16(y, l, g: StreamState, p: dict, *, h_init, nargout: int = 3):
+    """[x_hat_i, d_hat_i, x_tilde, g] = bnmf_sep_event_RT_IS16(y, l, g, p)    src/bnmf_sep_event_RT_IS16.m:1-423.
+    y: framelength samples (ch = 1); l: 1-based hop index; h_init: rand(R_x+R_d, 1) after rand('seed', p.random_seed).
+    With nargout <= 3 and callers that discard x_hat_i / d_hat_i (filewise_run_IS16.m:142) pass nargout=1 to skip the
+    two extra ISTFTs: they are then returned as None."""
+    ps = g._ps
+    y = _f64(np.asarray(y, dtype=np.float64).ravel())
+    if y.size != ps.framelength:
+        raise ValueError("y must hold p.framelength samples")
+    h0 = _f64(np.asarray(h_init, dtype=np.float64).ravel())
+    xt = np.empty(ps.framelength)
+    xh = dh = None
+    if nargout >= 2:
+        xh = np.empty((ps.EVENT_NUM, ps.framelength), order="C")
+        dh = np.empty((ps.NOISE_NUM, ps.framelength), order="C")
+    check(g.ctx._lib.snmfnat_stream_step(g._h, _dptr(y), int(l), _dptr(h0), _dptr(xt), _dptr(xh), _dptr(dh)))
+    if xh is not None:
+        xh = xh.reshape(ps.EVENT_NUM, 1, ps.framelength)      # :373-380 (3-D for compatibility with the NTF functions)
+        dh = dh.reshape(1, ps.NOISE_NUM, ps.framelength)
+    return xh, dh, xt, g

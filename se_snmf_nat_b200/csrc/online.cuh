@@ -37,7 +37,8 @@ struct SlotState {
   double* Ad_blk;               // [S][m_a][R_a]   ring (time-slot major)
   double* lam_blk;              // [S][m_a][LDF]   ring
   int* ring_head;               // [S] oldest time slot == next to overwrite
-  double* r_blk;                // [S][P_len_l][LDF] ring, slot (l-1) % P_len_l
+  double* r_blk;                // [S][P_len_l][LDF] ring
+  int* rblk_pos;                // [S] slot that receives the next column (the oldest one)
   double* lambda_dav;           // [S][LDF]
   double* Xm_tilde_prev;        // [S][LDF]
   int* update_switch;           // [S]

@@ -185,7 +185,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     }
     const double wn = sqrt(s2);
     wn_s[tid] = wn;
-    dph_s[tid] = fmax(s1 / wn + sc.sparsity, flr);
+    dph_s[tid] = 1.0 / fmax(s1 / wn + sc.sparsity, flr);   // reciprocal of the H-update denominator (:192-193)
     h_s[tid] = h_init[tid] * wn;
   }
   cluster.sync();  // everyone has read both exchange buffers before they are reused; publishes wn_s / h_s
@@ -240,7 +240,6 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     __syncthreads();
     // (R) ratio + cost terms for the CTA's rows (threads 0..127) and the tail rows (threads 128..128+E)
     if (warp < 5) {
-      double cterm = 0.0;
       const bool main_row = tid < HF_ROWS;
       const bool tail_row = tail_rank && tid >= HF_ROWS && tid < HF_ROWS + E;
       if (main_row || tail_row) {
@@ -252,13 +251,10 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
           lam = misc[16 + tid - HF_ROWS];
         }
         lam = fmax(lam, flr);
-        const double v = v_s[tid];
-        const double rr = v / lam;
-        if (sc.cost_check && it >= 1) cterm = v * log(rr) - v + lam;   // sparse_nmf.m:250
-        r_s[tid] = rr;
+        r_s[tid] = v_s[tid] * fast_rcp(lam);
+        // lambda is kept for the cost terms, which a spare warp evaluates during phase (B), off the critical path
+        if (main_row) lam_part[tid] = lam; else misc[16 + tid - HF_ROWS] = lam;
       }
-      cterm = warp_sum(cterm);
-      if (lane == 0) misc[warp] = cterm;
     }
     __syncthreads();
     // (B) g partial over this CTA's rows: lane <-> atom kB, half-warps split the rows, pairs of rows per step
@@ -295,7 +291,21 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
       s = warp_sum(s);
       if (lane == 0) misc[8] = s;
     } else if (warp == HF_WARPS - 2) {
-      if (lane == 0) xb[R] = ((misc[0] + misc[1]) + (misc[2] + misc[3])) + misc[4];
+      double cterm = 0.0;  // KL divergence terms of this CTA's rows                  sparse_nmf.m:250
+      if (sc.cost_check && it >= 1) {
+#pragma unroll
+        for (int j = 0; j < HF_ROWS / 32; ++j) {
+          const int f = lane + 32 * j;
+          const double v = v_s[f], lam = lam_part[f];
+          cterm += v * log(r_s[f]) - v + lam;
+        }
+        if (tail_rank && lane < E) {
+          const double v = v_s[HF_ROWS + lane], lam = misc[16 + lane];
+          cterm += v * log(r_s[HF_ROWS + lane]) - v + lam;
+        }
+      }
+      cterm = warp_sum(cterm);
+      if (lane == 0) xb[R] = cterm;
     }
     cluster.sync();
     // (C) combine the 4 CTAs in rank order, convergence test, h update
@@ -315,7 +325,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     }
     if (it >= sc.max_iter) stop = true;
     if (stop) break;
-    if (tid < R) h_s[tid] = h_s[tid] * gk / dph_s[tid];                   // :195
+    if (tid < R) h_s[tid] = h_s[tid] * gk * dph_s[tid];                   // :195
     __syncthreads();
     buf ^= 1;
     ++it;

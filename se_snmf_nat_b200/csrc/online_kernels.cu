@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include "online.cuh"
+#include "blk_sparse.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -342,58 +343,8 @@ gain_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, TraceA
 
   // ---- blk_sparse (src/blk_sparse.m:10-36) ----
   if (sc.blk_sparse) {
-    double mx = -INFINITY;
-    for (int f = tid; f < F; f += GN_THREADS) {
-      const double s = Xh[f] / fmax(Dh[f], flr);
-      rs1[f] = s;
-      mx = fmax(mx, s);
-    }
-    mx = block_max(mx, scratch);
-    double* rb = st.r_blk + (size_t)slot * PL * LDF;
-    const int cur = (l - 1) % PL;
-    for (int f = tid; f < F; f += GN_THREADS) rb[(size_t)cur * LDF + f] = rs1[f] / mx;
-    for (int f = tid; f < F; f += GN_THREADS) Q_s[f] = (f < sc.DCbin) ? 0.0 : 0.1;
-    __syncthreads();
-    if (l > PL) {
-      for (int f = tid; f < F; f += GN_THREADS) {
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < PL; ++i) {  // oldest column first
-          const double x = rb[(size_t)((l + i) % PL) * LDF + f];
-          a += x;
-          b = fma(x, x, b);
-        }
-        rs1[f] = a;
-        rs2[f] = b;
-      }
-      __syncthreads();
-      const int k2 = sc.P_len_k / 2;
-      const int kfirst = k2 + sc.DCbin;  // 1-based centre of the first window
-      const int nwin = (F - k2 >= kfirst) ? (F - k2 - kfirst) / sc.blk_gap + 1 : 0;
-      const double sqn = sqrt((double)(sc.P_len_l * sc.P_len_k));
-      for (int w = tid; w < nwin; w += GN_THREADS) {
-        const int k = kfirst + w * sc.blk_gap;
-        double l1 = 0.0, l2 = 0.0;
-        for (int f = k - k2; f < k + k2; ++f) {  // rows k-k2+1 .. k+k2 (1-based)
-          l1 += rs1[f];
-          l2 += rs2[f];
-        }
-        P_s[w] = (sqn - l1 / sqrt(l2)) / (sqn - 1.0);
-      }
-      __syncthreads();
-      if (tid == 0) {  // the fill is order dependent (Q(k-1) may have been written by the previous window)
-        const int g2 = (sc.blk_gap - 1) / 2;
-        for (int w = 0; w < nwin; ++w) {
-          const int k = kfirst + w * sc.blk_gap;
-          const double pv = sc.alpha_p * Q_s[k - 2] + (1.0 - sc.alpha_p) * P_s[w];
-          for (int q = k - 1 - g2; q <= k - 1 + g2; ++q)
-            if (q >= 0 && q < F) Q_s[q] = pv;
-        }
-        const double q0 = Q_s[sc.P_len_k + sc.DCbin - 1];
-        for (int q = 0; q < sc.P_len_k - 1 && q < F; ++q) Q_s[q] = q0;
-      }
-      __syncthreads();
-    }
-    for (int f = tid; f < sc.DCbin && f < F; f += GN_THREADS) Q_s[f] = 0.0;
+    blk_sparse_dev(Xh, Dh, st.r_blk + (size_t)slot * PL * LDF, LDF, F, l, st.rblk_pos[slot], sc, Q_s, rs1, rs2, P_s, scratch);
+    if (tid == 0) st.rblk_pos[slot] = (st.rblk_pos[slot] + 1) % PL;   // every thread has read it (barriers inside)
   } else {
     for (int f = tid; f < F; f += GN_THREADS) Q_s[f] = 1.0;
   }

@@ -75,7 +75,7 @@ void SlotBuffers::alloc(int S_, const OnlineDims& d_) {
   G.alloc((size_t)S * LDF);
   h_cost.alloc(S);
   h_init.alloc(d.R);
-  bd_sel.alloc(S); ring_head.alloc(S); update_switch.alloc(S); h_iters.alloc(S); gated.alloc(S);
+  rblk_pos.alloc(S); bd_sel.alloc(S); ring_head.alloc(S); update_switch.alloc(S); h_iters.alloc(S); gated.alloc(S);
   do_update.alloc(S); n_up.alloc(S); w_iters.alloc(S); err_flag.alloc(1);
   idx_up.alloc((size_t)S * (d.R_a > 0 ? d.R_a : 1));
   idx_rem.alloc((size_t)S * (d.R_a > 0 ? d.R_a : 1));
@@ -113,7 +113,7 @@ void SlotBuffers::reset(snmfnat_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   lam_blk.zero(st); r_blk.zero(st); lambda_dav.zero(st); Xm_tilde_prev.zero(st);
   A.zero(st); Xhat.zero(st); Dhat.zero(st); Q.zero(st); G.zero(st); h_cost.zero(st);
-  bd_sel.zero(st); ring_head.zero(st); h_iters.zero(st); gated.zero(st); do_update.zero(st); n_up.zero(st);
+  rblk_pos.zero(st); bd_sel.zero(st); ring_head.zero(st); h_iters.zero(st); gated.zero(st); do_update.zero(st); n_up.zero(st);
   w_iters.zero(st); err_flag.zero(st); idx_up.zero(st); idx_rem.zero(st); stats.zero(st);
   fill_int_kernel<<<(S + 255) / 256, 256, 0, st>>>(update_switch.p, S, 1);  // init_buff.m:41
   count_launch(ctx);
@@ -135,7 +135,7 @@ SlotState SlotBuffers::view() const {
   v.bdfix_stride = 0;
   v.Bd[0] = Bd0.p; v.Bd[1] = Bd1.p;
   v.bd_sel = bd_sel.p;
-  v.Ad_blk = Ad_blk.p; v.lam_blk = lam_blk.p; v.ring_head = ring_head.p; v.r_blk = r_blk.p;
+  v.Ad_blk = Ad_blk.p; v.lam_blk = lam_blk.p; v.ring_head = ring_head.p; v.r_blk = r_blk.p; v.rblk_pos = rblk_pos.p;
   v.lambda_dav = lambda_dav.p; v.Xm_tilde_prev = Xm_tilde_prev.p; v.update_switch = update_switch.p;
   v.A = A.p; v.Xhat = Xhat.p; v.Dhat = Dhat.p; v.Q = Q.p; v.G = G.p;
   v.h_iters = h_iters.p; v.h_cost = h_cost.p; v.gated = gated.p; v.do_update = do_update.p; v.n_up = n_up.p;

@@ -20,7 +20,7 @@ struct SlotBuffers {
   OnlineDims d{};
   DevBuf<double> Bx, Bd_fix, Bd0, Bd1, Ad_blk, Ad_init, lam_blk, r_blk, lambda_dav, Xm_tilde_prev;
   DevBuf<double> A, Xhat, Dhat, Q, G, h_cost, h_init, win_stft, win_istft;
-  DevBuf<int> bd_sel, ring_head, update_switch, h_iters, gated, do_update, n_up, idx_up, idx_rem, w_iters, err_flag;
+  DevBuf<int> rblk_pos, bd_sel, ring_head, update_switch, h_iters, gated, do_update, n_up, idx_up, idx_rem, w_iters, err_flag;
   DevBuf<int> l_offset, n_hops;
   DevBuf<long long> frame_base;
   DevBuf<unsigned long long> stats;

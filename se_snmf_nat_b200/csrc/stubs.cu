@@ -13,15 +13,4 @@ int snmfnat_train_reset(snmfnat_train*) SN_STUB("snmfnat_train_reset")
 int snmfnat_train_iterate(snmfnat_train*, int, double*, double*) SN_STUB("snmfnat_train_iterate")
 int snmfnat_train_get_w(snmfnat_train*, float*) SN_STUB("snmfnat_train_get_w")
 int snmfnat_train_get_h(snmfnat_train*, float*, int64_t, int64_t) SN_STUB("snmfnat_train_get_h")
-int snmfnat_sparse_nmf(snmfnat_ctx*, const double*, int, int, int, const snmfnat_nmf_opts*, const double*, const double*, const double*, const uint8_t*, const uint8_t*, double*, double*, double*, double*, int*) SN_STUB("snmfnat_sparse_nmf")
-int snmfnat_snmf_mdi(snmfnat_ctx*, const double*, const double*, int, int, int, int, const snmfnat_nmf_opts*, const double*, const double*, const double*, const uint8_t*, const uint8_t*, double*, double*, double*, double*, int*) SN_STUB("snmfnat_snmf_mdi")
-int snmfnat_dnmf_adapt(snmfnat_ctx*, const double*, const double*, const double*, int, int, int, int, const snmfnat_nmf_opts*, const double*, const double*, double*) SN_STUB("snmfnat_dnmf_adapt")
-int snmfnat_stft_fft(snmfnat_ctx*, const double*, int64_t, int, int, int, int, const double*, double, double*, double*) SN_STUB("snmfnat_stft_fft")
-int snmfnat_synth_ifft_buff(snmfnat_ctx*, const double*, const double*, int, int, int, int, const double*, double, int, double, double*) SN_STUB("snmfnat_synth_ifft_buff")
-int snmfnat_blk_sparse(snmfnat_ctx*, const double*, const double*, const double*, int, int, const snmfnat_params*, double*, double*) SN_STUB("snmfnat_blk_sparse")
-int snmfnat_stream_create(snmfnat_ctx*, const snmfnat_params*, const double*, const double*, const double*, const double*, int, const double*, const double*, int, const double*, const double*, snmfnat_stream**) SN_STUB("snmfnat_stream_create")
-int snmfnat_stream_destroy(snmfnat_stream*) SN_STUB("snmfnat_stream_destroy")
-int snmfnat_stream_step(snmfnat_stream*, const double*, int, const double*, double*, double*, double*) SN_STUB("snmfnat_stream_step")
-int snmfnat_stream_get(snmfnat_stream*, const char*, double*, int64_t) SN_STUB("snmfnat_stream_get")
-int snmfnat_stream_set(snmfnat_stream*, const char*, const double*, int64_t) SN_STUB("snmfnat_stream_set")
 }

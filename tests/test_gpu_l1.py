@@ -1,0 +1,212 @@
+"""GPU parity of the L1 / L2 entry points (sparse_nmf, snmf_mdi, DNMF_adapt, stft_fft, synth_ifft_buff, blk_sparse,
+init_buff + bnmf_sep_event_RT_IS16) against the float64 oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, snr_db
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3   # north_star: H/W relative error; float64 kernels are expected near 1e-12
+
+
+@pytest.fixture(scope="module")
+def api():
+    from se_snmf_nat_b200 import api as a
+    return a
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import snmf_oracle
+    return snmf_oracle
+
+
+def _rand_from(rs):
+    return lambda m, n: rs.rand(n, m).T.copy()     # column-major fill like MATLAB's rand(m, n)
+
+
+@pytest.mark.parametrize("cf,wu,hu", [("kl", True, True), ("kl", False, True), ("kl", True, False), ("ed", True, True),
+                                      ("is", True, True), ("beta1.5", True, True)])
+def test_sparse_nmf_matches_oracle(api, O, cf, wu, hu):
+    rs = np.random.RandomState(0)
+    F, n, r = 97, 45, 12
+    V = rs.gamma(1.0, 1.0, size=(F, n)) + 1e-3
+    w0, h0 = rs.rand(F, r) + 0.05, rs.rand(r, n) + 0.05
+    p = dict(init_w=w0, init_h=h0, max_iter=40, conv_eps=1e-4, sparsity=0.3, cost_check=1, cf=cf if cf != "beta1.5" else "x",
+             w_update_ind=np.full(r, wu), h_update_ind=np.full(r, hu))
+    kw = dict(cf=cf) if cf != "beta1.5" else dict(cf="x", beta=1.5)
+    if cf == "beta1.5":
+        p["beta"] = 1.5
+    w, h, obj = api.sparse_nmf(V, p)
+    wo, ho, oo = O.sparse_nmf(V, init_w=w0, init_h=h0, max_iter=40, conv_eps=1e-4, sparsity=0.3,
+                              w_update_ind=np.full(r, wu), h_update_ind=np.full(r, hu), **kw)
+    assert obj["iters"] == oo["iters"]
+    assert rel_err(wo, w) < 1e-9 and rel_err(ho, h) < 1e-9
+    assert np.allclose(obj["cost"], oo["cost"], rtol=1e-10)
+    assert np.allclose(obj["div"], oo["div"], rtol=1e-10)
+
+
+def test_sparse_nmf_partial_indices_and_matrix_sparsity(api, O):
+    rs = np.random.RandomState(1)
+    F, n, r = 64, 30, 10
+    V = rs.gamma(1.0, 1.0, size=(F, n)) + 1e-3
+    w0, h0 = rs.rand(F, r) + 0.05, rs.rand(r, n) + 0.05
+    wi = np.arange(r) % 2 == 0
+    hi = np.arange(r) < 7
+    sp = rs.rand(r, n)
+    p = dict(init_w=w0, init_h=h0, max_iter=25, conv_eps=0, sparsity=sp, cost_check=1, w_update_ind=wi, h_update_ind=hi)
+    w, h, obj = api.sparse_nmf(V, p)
+    wo, ho, oo = O.sparse_nmf(V, init_w=w0, init_h=h0, max_iter=25, conv_eps=0, sparsity=sp, w_update_ind=wi, h_update_ind=hi)
+    assert obj["iters"] == 25 and rel_err(wo, w) < 1e-9 and rel_err(ho, h) < 1e-9
+    # rows of h outside h_ind only get the initial rescaling by the column norms
+    assert np.allclose(h[7:], h0[7:] * np.linalg.norm(w0, axis=0)[7:, None])
+
+
+def test_sparse_nmf_requires_inits_and_cost_check(api):
+    V = np.ones((8, 4))
+    with pytest.raises(KeyError):
+        api.sparse_nmf(V, dict(init_w=np.ones((8, 2)), init_h=np.ones((2, 4))))
+    with pytest.raises(ValueError):
+        api.sparse_nmf(V, dict(cost_check=1))
+    with pytest.raises(ValueError):
+        api.sparse_nmf(V, dict(cost_check=1, r=3))      # no rand= given
+
+
+def test_sparse_nmf_online_shapes(api, O, bases, rng_inputs):
+    """The two shapes of the online path through the generic entry: 513 x 1 H-solve and 513 x 100 W-solve."""
+    h_init, Ad = rng_inputs
+    rs = np.random.RandomState(2)
+    W = np.concatenate([bases["B_DFT_x"], bases["B_DFT_d"]], axis=1)
+    v = W @ rs.gamma(0.5, 1.0, size=(200, 1)) * 1e6 + 1e-9
+    p = dict(init_w=W, init_h=h_init, max_iter=100, conv_eps=1e-3, sparsity=5.0, cost_check=1,
+             w_update_ind=np.zeros(200, bool), h_update_ind=np.ones(200, bool))
+    w, h, obj = api.sparse_nmf(v, p)
+    wo, ho, oo = O.sparse_nmf(v, init_w=W, init_h=h_init, max_iter=100, conv_eps=1e-3, sparsity=5.0,
+                              w_update_ind=np.zeros(200, bool), h_update_ind=np.ones(200, bool))
+    assert obj["iters"] == oo["iters"] and rel_err(ho, h) < 1e-9
+    V = rs.gamma(1.0, 1e5, size=(513, 100))
+    p = dict(init_w=bases["B_DFT_d"][:, :41], init_h=Ad[:41], max_iter=100, conv_eps=1e-3, sparsity=5.0, cost_check=1,
+             w_update_ind=np.ones(41, bool), h_update_ind=np.zeros(41, bool))
+    w, h, obj = api.sparse_nmf(V, p)
+    wo, ho, oo = O.sparse_nmf(V, init_w=bases["B_DFT_d"][:, :41], init_h=Ad[:41], max_iter=100, conv_eps=1e-3,
+                              sparsity=5.0, w_update_ind=np.ones(41, bool), h_update_ind=np.zeros(41, bool))
+    assert obj["iters"] == oo["iters"] and rel_err(wo, w) < 1e-9
+    assert np.allclose(np.linalg.norm(w, axis=0), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_snmf_mdi(api, O, soft):
+    rs = np.random.RandomState(3)
+    W = rs.rand(50, 8)
+    V = W @ rs.rand(8, 12) + 1e-9
+    Dm = rs.rand(50, 12) if soft else (rs.rand(50, 12) > 0.3).astype(float)
+    h0 = rs.rand(8, 12)
+    p = dict(init_w=W, init_h=h0, w_update_ind=np.zeros(8, bool), h_update_ind=np.ones(8, bool), sparsity_mdi=0.1,
+             conv_eps_mdi=1e-6, max_iter=60, cost_check=1)
+    vm, h, obj = api.snmf_mdi(V, Dm, p, soft=soft)
+    vo, ho, oo = O.snmf_mdi(V, Dm, soft_mask=soft, init_w=W, init_h=h0, w_update_ind=np.zeros(8, bool),
+                            h_update_ind=np.ones(8, bool), sparsity_mdi=0.1, conv_eps_mdi=1e-6, max_iter=60)
+    assert obj["iters"] == oo["iters"]
+    assert rel_err(vo, vm) < 1e-9 and rel_err(ho, h) < 1e-9
+    with pytest.raises(KeyError):
+        api.snmf_mdi(V, Dm, dict(init_w=W, init_h=h0, cost_check=1))
+
+
+def test_dnmf_adapt(api, O):
+    rs = np.random.RandomState(4)
+    F, n, Rx, Rd = 80, 40, 6, 5
+    B = rs.rand(F, Rx + Rd) + 0.01
+    Y = B @ rs.gamma(0.5, 1.0, size=(Rx + Rd, n)) + 1e-6
+    D = B[:, Rx:] @ rs.gamma(0.5, 1.0, size=(Rd, n)) + 1e-6
+    p = dict(R_x=Rx, R_d=Rd, max_iter=30, conv_eps=1e-4, sparsity=0.5, cost_check=1)
+    Ba = api.DNMF_adapt(Y, D, B, p, rand=_rand_from(np.random.RandomState(9)))
+    Bo = O.dnmf_adapt(Y, D, B, R_x=Rx, R_d=Rd, rand=_rand_from(np.random.RandomState(9)), max_iter=30, conv_eps=1e-4,
+                      sparsity=0.5)
+    assert Ba.shape == (F, Rd) and rel_err(Bo, Ba) < 1e-9
+
+
+@pytest.mark.parametrize("preemph", [0.0, 0.92])
+def test_stft_fft_and_synth(api, O, preemph):
+    po = O.default_params()
+    s = np.random.RandomState(5).randn(16000 * 2 + 77) * 1000
+    mag, ph = api.stft_fft(s, 640, 160, 1024, 5, po["win_STFT"], preemph)
+    mo, pho = O.stft_fft(s, 640, 160, 1024, 5, po["win_STFT"], preemph)
+    assert mag.shape == mo.shape
+    assert rel_err(mo, mag) < 1e-12
+    nv = int(np.sum(np.any(mo != 0, axis=0)))
+    assert np.all(mag[:, nv:] == 0) and np.all(ph[:, nv:] == 0)      # trailing preallocated columns stay zero
+    d = np.angle(np.exp(1j * (ph[:, :nv] - pho[:, :nv])))
+    assert np.max(np.abs(d[mo[:, :nv] > 1e-3])) < 1e-9
+    # resynthesis of 50 frames, half-spectrum and full-spectrum input forms (synth_ifft_buff.m:13-19)
+    P = mo[:, :50] ** 2
+    sb = api.synth_ifft_buff(P, pho[:, :50], 640, 1024, po["win_ISTFT"], preemph, 5, 2.0)
+    so = O.synth_ifft_buff(P, pho[:, :50], 640, 1024, po["win_ISTFT"], preemph, 5, 2.0)
+    assert rel_err(so, sb) < 1e-10
+    full = np.random.RandomState(6).rand(1024, 7)
+    sb = api.synth_ifft_buff(full, None, 640, 1024, po["win_ISTFT"], 0.0, 5, 1.0)
+    so = O.synth_ifft_buff(full, np.zeros_like(full), 640, 1024, po["win_ISTFT"], 0.0, 5, 1.0)
+    assert rel_err(so, sb) < 1e-10
+
+
+@pytest.mark.parametrize("l,gap", [(5, 3), (25, 3), (25, 1), (40, 5)])
+def test_blk_sparse(api, O, l, gap):
+    rs = np.random.RandomState(7)
+    p = dict(api.default_p(), blk_gap=gap)
+    po = dict(O.default_params(), blk_gap=gap)
+    r_blk = rs.rand(513, 20)
+    X, D = rs.rand(513) + 0.1, rs.rand(513) * (rs.rand(513) > 0.1)
+    Q, rout = api.blk_sparse(X, D, r_blk, l, p)
+    Qo, ro = O.blk_sparse(X, D, r_blk, l, po)
+    assert np.allclose(rout, ro, rtol=1e-14, atol=0)
+    assert np.allclose(Q, Qo, rtol=1e-12, atol=1e-15)
+
+
+def test_per_hop_stream_matches_oracle_and_batch(api, O, bases, wavs, rng_inputs):
+    """config 2 (latency path): init_buff + bnmf_sep_event_RT_IS16 hop by hop == oracle == batch path."""
+    h_init, Ad = rng_inputs
+    p = api.default_p()
+    po = O.default_params()
+    pcm = wavs["LM_in"][16000:16000 + 160 * 90]
+    Bx, Bd = bases["B_DFT_x"], bases["B_DFT_d"]
+    g = api.init_buff(Bx, Bd, Bx, Bd, p, Ad_blk_init=Ad)
+    go = O.init_buff(Bx, Bd, Bx, Bd, po, Ad_blk_init=Ad)
+    y = np.zeros(640)
+    n_full = len(pcm) // 160
+    frames = []
+    for l in range(1, n_full + 4 + 1):
+        if l <= n_full:
+            y = np.concatenate([y[160:], pcm[(l - 1) * 160:l * 160].astype(float)])
+        else:
+            y = np.zeros(640)
+        want_aux = l in (30, 60)
+        xh, dh, xt, g = api.bnmf_sep_event_RT_IS16(y, l, g, p, h_init=h_init, nargout=3 if want_aux else 1)
+        xho, dho, xto, go = O.bnmf_sep_event_RT_IS16(y, l, go, po, h_init=h_init, want_aux=want_aux)
+        st = g["stats"]
+        assert int(st[0]) == go.dbg["h_iters"], l
+        assert bool(st[1]) == go.dbg["gated"] and int(st[2]) == go.dbg["R_a_up"] and int(st[3]) == go.dbg["w_iters"]
+        assert np.max(np.abs(xt - xto)) <= 1e-6 * max(1.0, np.max(np.abs(xto))), l
+        if want_aux:
+            assert xh.shape == (1, 1, 640) and dh.shape == (1, 1, 640)
+            assert np.max(np.abs(xh[0, 0] - xho[0])) <= 1e-6 * max(1.0, np.max(np.abs(xho)))
+            assert np.max(np.abs(dh[0, 0] - dho[0])) <= 1e-6 * max(1.0, np.max(np.abs(dho)))
+        frames.append(xt)
+    for name, ref in (("B_DFT_d", go.B_DFT_d), ("Ad_blk", go.Ad_blk), ("lambda_d_blk", go.lambda_d_blk),
+                      ("r_blk", go.r_blk), ("lambda_dav", go.lambda_dav), ("Xm_tilde", go.Xm_tilde), ("Ym", go.Ym)):
+        assert rel_err(ref, g[name]) < 1e-9, name
+    assert np.max(np.abs(np.angle(np.exp(1j * (g["Yp"] - go.Yp))))[go.Ym > 1e-3]) < 1e-9
+    # state write-back round trip (what a MATLAB caller does with B_D_u.mat)
+    B = g["B_DFT_d"]
+    g["B_DFT_d"] = B
+    g["Ad_blk"] = g["Ad_blk"]
+    assert np.array_equal(g["B_DFT_d"], B)
+    assert rel_err(go.lambda_d_blk, g["lambda_d_blk"]) < 1e-9
+    # same signal through the batch path
+    out = api.enhance_batch([pcm], p, Bx, Bd, h_init=h_init, Ad_blk_init=Ad)[0]
+    ola = np.zeros(640)
+    ref = []
+    for l, fr in enumerate(frames, start=1):
+        if l > 3:
+            ola = np.concatenate([ola[160:], np.zeros(160)]) + fr
+            ref.append(O.to_int16(ola[:160]))
+    assert np.abs(np.concatenate(ref).astype(int) - out.astype(int)).max() <= 1
+    g.close()
