@@ -2,7 +2,7 @@
  * snmfnat.h -- C ABI of libsnmfnat.so: the B200-native (sm_100a) implementation of the
  * SE_SNMF_NAT enhancement hot path.  This is the drop-in boundary: every entry point
  * replaces one MATLAB function of the reference (cited as file:line relative to the
- * reference root) and is what that function's MEX gateway (mex/*.cpp) binds.
+ * reference root) and is what that function's MEX gateway (the .cpp files under mex/) binds.
  *
  * Conventions
  *   - plain C: opaque handles, pointers and sizes; no C++/torch types.
@@ -249,7 +249,7 @@ int snmfnat_train_set_data(snmfnat_train* t, const float* V, int v_on_device, co
 void* snmfnat_train_dev_ptr(snmfnat_train* t, const char* which);
 /* Re-run the init of sparse_nmf.m:157-169 (normalise W, rescale H, first lambda) on the resident data. */
 int snmfnat_train_reset(snmfnat_train* t);
-/* One MU iteration (H-update, W-update + all-reduce, cost).  *cost/*div may be NULL. */
+/* One MU iteration (H-update, W-update + all-reduce, cost).  cost and div may be NULL. */
 int snmfnat_train_iterate(snmfnat_train* t, int n_iters, double* div, double* cost);
 int snmfnat_train_get_w(snmfnat_train* t, float* w);
 int snmfnat_train_get_h(snmfnat_train* t, float* h, int64_t t0, int64_t count);

@@ -1,0 +1,76 @@
+// MEX gateway: snmfnat_enhance_files(paths_in, paths_out, B_DFT_x, B_DFT_d, p [, chain_id])
+// The hop loops of filewise_run_IS16.m:54-186 / src/NTF_sep_event_RT.m:12-156 for a whole list of files in ONE device
+// call (no per-hop PCIe crossing): reads the int16 samples after the 44-byte WAV header (:92-97), enhances them with
+// snmfnat_enhance_batch, writes 16-bit mono WAV files.  chain_id (optional, one per file) reproduces the B_D_u.mat
+// carry-over of run_ntf_sep_RT: files with equal id are processed in list order on one adapted noise dictionary.
+#include <cstdio>
+#include "snmfnat_mex.h"
+using namespace snmex;
+
+static std::vector<int16_t> read_pcm(const std::string& path) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) mexErrMsgIdAndTxt("snmfnat:io", "cannot open %s", path.c_str());
+  std::fseek(f, 0, SEEK_END);
+  long bytes = std::ftell(f);
+  std::fseek(f, 44, SEEK_SET);                       // 22 int16 of header (filewise_run_IS16.m:93-96)
+  std::vector<int16_t> v(bytes > 44 ? (bytes - 44) / 2 : 0);
+  if (!v.empty() && std::fread(v.data(), 2, v.size(), f) != v.size()) mexErrMsgIdAndTxt("snmfnat:io", "short read on %s", path.c_str());
+  std::fclose(f);
+  return v;
+}
+static void write_wav(const std::string& path, const std::vector<int16_t>& x, int fs) {
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) mexErrMsgIdAndTxt("snmfnat:io", "cannot create %s", path.c_str());
+  const uint32_t data = (uint32_t)x.size() * 2, riff = 36 + data, fmt = 16, rate = fs, brate = fs * 2;
+  const uint16_t pcm = 1, ch = 1, align = 2, bits = 16;
+  std::fwrite("RIFF", 1, 4, f); std::fwrite(&riff, 4, 1, f); std::fwrite("WAVEfmt ", 1, 8, f); std::fwrite(&fmt, 4, 1, f);
+  std::fwrite(&pcm, 2, 1, f); std::fwrite(&ch, 2, 1, f); std::fwrite(&rate, 4, 1, f); std::fwrite(&brate, 4, 1, f);
+  std::fwrite(&align, 2, 1, f); std::fwrite(&bits, 2, 1, f); std::fwrite("data", 1, 4, f); std::fwrite(&data, 4, 1, f);
+  std::fwrite(x.data(), 2, x.size(), f);
+  std::fclose(f);
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  (void)plhs;
+  if (nrhs < 5 || nlhs > 0) mexErrMsgIdAndTxt("snmfnat:usage", "snmfnat_enhance_files(paths_in,paths_out,B_DFT_x,B_DFT_d,p[,chain_id])");
+  if (!mxIsCell(prhs[0]) || !mxIsCell(prhs[1])) mexErrMsgIdAndTxt("snmfnat:usage", "paths must be cell arrays of strings");
+  const size_t n = mxGetNumberOfElements(prhs[0]);
+  const mxArray* p = prhs[4];
+  const snmfnat_params q = params(p);
+  const size_t F = q.fftlength / 2 + 1, R = q.R_x + q.R_d;
+  std::vector<std::vector<int16_t>> pcm(n), out(n);
+  std::vector<const int16_t*> pin(n);
+  std::vector<int16_t*> pout(n);
+  std::vector<int64_t> len(n);
+  std::vector<std::string> po(n);
+  for (size_t i = 0; i < n; ++i) {
+    char* a = mxArrayToString(mxGetCell(prhs[0], i));
+    char* b = mxArrayToString(mxGetCell(prhs[1], i));
+    pcm[i] = read_pcm(a);
+    po[i] = b;
+    mxFree(a); mxFree(b);
+    len[i] = (int64_t)pcm[i].size();
+    out[i].resize((size_t)(len[i] / q.frameshift + 1) * q.frameshift);
+    pin[i] = pcm[i].data();
+    pout[i] = out[i].data();
+  }
+  std::vector<int32_t> chain;
+  if (nrhs > 5 && !mxIsEmpty(prhs[5])) for (size_t i = 0; i < n; ++i) chain.push_back((int32_t)mxGetPr(prhs[5])[i]);
+  // RNG on the host: H init after rand('seed',.), then one rand(R_a, m_a) per file like init_buff.m:38
+  seed_rng(p);
+  mxArray* h0 = host_rand(R, 1);
+  std::vector<double> ad((size_t)n * q.R_a * q.m_a);
+  for (size_t i = 0; i < n; ++i) {
+    mxArray* a = host_rand(q.R_a, q.m_a);
+    std::memcpy(ad.data() + i * q.R_a * q.m_a, mxGetPr(a), sizeof(double) * q.R_a * q.m_a);
+    mxDestroyArray(a);
+  }
+  const mxArray *ws = field(p, "win_STFT"), *wi = field(p, "win_ISTFT");
+  if (!ws || !wi) mexErrMsgIdAndTxt("snmfnat:param", "p.win_STFT / p.win_ISTFT missing");
+  check(snmfnat_enhance_batch(ctx(), &q, mxGetPr(ws), mxGetPr(wi), mat(prhs[2], F, q.R_x, "B_DFT_x"),
+                              mat(prhs[3], F, q.R_d, "B_DFT_d"), (int)F, (int)n, pin.data(), len.data(),
+                              chain.empty() ? nullptr : chain.data(), mxGetPr(h0), ad.data(),
+                              (int64_t)q.R_a * q.m_a, pout.data()));
+  mxDestroyArray(h0);
+  for (size_t i = 0; i < n; ++i) write_wav(po[i], out[i], q.fs);
+}

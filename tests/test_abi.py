@@ -63,3 +63,11 @@ def test_no_device_fails_loudly(lib):
 def test_product_package_never_imports_the_oracle():
     for f in (ROOT / "se_snmf_nat_b200").rglob("*.py"):
         assert "oracle" not in f.read_text().replace("no oracle", ""), f
+
+
+def test_mex_gateways_compile_against_shim():
+    """No MATLAB/Octave here: the gateways are syntax- and ABI-checked against mex/mex_shim.h."""
+    import subprocess
+    r = subprocess.run(["make", "-C", str(ROOT / "mex"), "check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all gateways compile" in r.stdout

@@ -193,7 +193,7 @@ def test_per_hop_stream_matches_oracle_and_batch(api, O, bases, wavs, rng_inputs
     for name, ref in (("B_DFT_d", go.B_DFT_d), ("Ad_blk", go.Ad_blk), ("lambda_d_blk", go.lambda_d_blk),
                       ("r_blk", go.r_blk), ("lambda_dav", go.lambda_dav), ("Xm_tilde", go.Xm_tilde), ("Ym", go.Ym)):
         assert rel_err(ref, g[name]) < 1e-9, name
-    assert np.max(np.abs(np.angle(np.exp(1j * (g["Yp"] - go.Yp))))[go.Ym > 1e-3]) < 1e-9
+    assert np.all(g["Yp"] == 0) and np.all(go.Yp == 0)      # the last flush hop is an all-zero frame
     # state write-back round trip (what a MATLAB caller does with B_D_u.mat)
     B = g["B_DFT_d"]
     g["B_DFT_d"] = B
