@@ -245,12 +245,25 @@ int snmfnat_train_nccl_unique_id(void* id128);
 int snmfnat_train_attach_nccl(snmfnat_train* t, const void* nccl_unique_id, int rank, int world);
 int snmfnat_train_set_data(snmfnat_train* t, const float* V, int v_on_device, const float* init_w,
                            const float* init_h, int h_on_device);
-/* Device pointers of the resident V / H / W (float32) so that a host side can fill them in place. */
+/* Device pointers of the resident arrays (float32) so that a host side can fill them in place:
+ * "V" [T_local][ldv] (frame-major, ldv >= F), "H" [T_local][Kp] (frame-major, Kp >= K, padding must stay 0),
+ * "W_init" [K][F] (the init_w staging read by snmfnat_train_reset), "W" [K][F] (current dictionary). */
 void* snmfnat_train_dev_ptr(snmfnat_train* t, const char* which);
-/* Re-run the init of sparse_nmf.m:157-169 (normalise W, rescale H, first lambda) on the resident data. */
+int snmfnat_train_get_layout(snmfnat_train* t, int* ldv, int* kp);
+/* Call after filling "V" in place: rebuilds the library's bin-major copy of V. */
+int snmfnat_train_commit_v(snmfnat_train* t);
+/* Re-run the init of sparse_nmf.m:157-160 (normalise W_init into W, rescale H) on the resident data. */
 int snmfnat_train_reset(snmfnat_train* t);
-/* One MU iteration (H-update, W-update + all-reduce, cost).  cost and div may be NULL. */
+/* n_iters MU iterations (H-update, W-update + all-reduce), sparse_nmf.m:186-244.  div / cost (n_iters doubles each,
+ * sparse_nmf.m:250,261) may be NULL; asking for them costs one stream synchronisation per iteration. */
 int snmfnat_train_iterate(snmfnat_train* t, int n_iters, double* div, double* cost);
+/* The whole loop of sparse_nmf.m:186-286 with its stop rule (:273-283): at most max_iter iterations, stops after
+ * iteration it > 1 when |cost - last_cost| / last_cost < conv_eps.  div / cost hold max_iter doubles (may be NULL),
+ * *iters = executed iterations. */
+int snmfnat_train_run(snmfnat_train* t, int max_iter, double conv_eps, double* div, double* cost, int* iters);
+/* The all-reduced W-update accumulators of the last iteration: g = (V ./ (W*H)) * H' (F x K, sparse_nmf.m:217) and
+ * hs = sum(H,2) (K); either may be NULL. */
+int snmfnat_train_get_acc(snmfnat_train* t, float* g, float* hs);
 int snmfnat_train_get_w(snmfnat_train* t, float* w);
 int snmfnat_train_get_h(snmfnat_train* t, float* h, int64_t t0, int64_t count);
 

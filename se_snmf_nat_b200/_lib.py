@@ -130,8 +130,12 @@ SIGNATURES = {
     "snmfnat_train_attach_nccl": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "snmfnat_train_set_data": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int]),
     "snmfnat_train_dev_ptr": (_vp, [_vp, C.c_char_p]),
+    "snmfnat_train_get_layout": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int)]),
+    "snmfnat_train_commit_v": (C.c_int, [_vp]),
     "snmfnat_train_reset": (C.c_int, [_vp]),
     "snmfnat_train_iterate": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "snmfnat_train_run": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _dp, _P(C.c_int)]),
+    "snmfnat_train_get_acc": (C.c_int, [_vp, _fp, _fp]),
     "snmfnat_train_get_w": (C.c_int, [_vp, _fp]),
     "snmfnat_train_get_h": (C.c_int, [_vp, _fp, C.c_int64, C.c_int64]),
 }

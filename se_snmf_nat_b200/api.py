@@ -566,3 +566,121 @@ def bnmf_sep_event_RT_IS16(y, l, g: StreamState, p: dict, *, h_init, nargout: in
         xh = xh.reshape(ps.EVENT_NUM, 1, ps.framelength)      # :373-380 (3-D for compatibility with the NTF functions)
         dh = dh.reshape(1, ps.NOISE_NUM, ps.framelength)
     return xh, dh, xt, g
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# offline dictionary training (run_basis_train.m:80-91,112-116) -- frame-sharded, tf32 tensor cores
+# ----------------------------------------------------------------------------------------------------------------
+class Train:
+    """Frame shard of one `sparse_nmf(TF_mag, p)` call with W and H both updated (run_basis_train.m:84-88),
+    resident on one GPU.  V is F x T_local, init_w F x K, init_h K x T_local (MATLAB layouts; float32 on the device)."""
+
+    def __init__(self, ctx: Context, F: int, K: int, T_local: int, sparsity: float):
+        self._lib = _lib.load()
+        self.ctx = ctx
+        self.F, self.K, self.T = int(F), int(K), int(T_local)
+        h = C.c_void_p()
+        check(self._lib.snmfnat_train_create(ctx._h, self.F, self.K, self.T, float(sparsity), 1, C.byref(h)))
+        self._h = h
+        ldv, kp = C.c_int(), C.c_int()
+        check(self._lib.snmfnat_train_get_layout(self._h, C.byref(ldv), C.byref(kp)))
+        self.ldv, self.Kp = ldv.value, kp.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.snmfnat_train_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def attach_nccl(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(self._lib.snmfnat_train_attach_nccl(self._h, C.cast(buf, C.c_void_p), int(rank), int(world)))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_lib.load().snmfnat_train_nccl_unique_id(C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def set_data(self, V=None, init_w=None, init_h=None):
+        """Host arrays in MATLAB shapes (F x T, F x K, K x T)."""
+        def f32(a, shape):
+            if a is None:
+                return None, None
+            a = np.asfortranarray(np.asarray(a, dtype=np.float32))
+            assert a.shape == shape, (a.shape, shape)
+            return a, a.ctypes.data_as(C.c_void_p)
+        v, vp = f32(V, (self.F, self.T))
+        w, wp = f32(init_w, (self.F, self.K))
+        h, hp = f32(init_h, (self.K, self.T))
+        check(self._lib.snmfnat_train_set_data(self._h, vp, 0, wp, hp, 0))
+
+    def dev_ptr(self, which: str) -> int:
+        return int(self._lib.snmfnat_train_dev_ptr(self._h, which.encode()) or 0)
+
+    def reset(self):
+        check(self._lib.snmfnat_train_reset(self._h))
+
+    def iterate(self, n: int, want_cost: bool = False):
+        if not want_cost:
+            check(self._lib.snmfnat_train_iterate(self._h, int(n), None, None))
+            return None
+        div = np.zeros(n)
+        cost = np.zeros(n)
+        check(self._lib.snmfnat_train_iterate(self._h, int(n), _dptr(div), _dptr(cost)))
+        return dict(div=div, cost=cost)
+
+    def run(self, max_iter: int, conv_eps: float):
+        div = np.zeros(max_iter)
+        cost = np.zeros(max_iter)
+        its = C.c_int()
+        check(self._lib.snmfnat_train_run(self._h, int(max_iter), float(conv_eps), _dptr(div), _dptr(cost), C.byref(its)))
+        n = its.value
+        return dict(div=div[:n], cost=cost[:n], iters=n)
+
+    def get_w(self) -> np.ndarray:
+        w = np.zeros((self.F, self.K), dtype=np.float32, order="F")
+        check(self._lib.snmfnat_train_get_w(self._h, w.ctypes.data_as(C.POINTER(C.c_float))))
+        return w
+
+    def get_acc(self):
+        g = np.zeros((self.F, self.K), dtype=np.float32, order="F")
+        hs = np.zeros(self.K, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        check(self._lib.snmfnat_train_get_acc(self._h, g.ctypes.data_as(fp), hs.ctypes.data_as(fp)))
+        return g, hs
+
+    def get_h(self, t0: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.T - t0 if count is None else count
+        h = np.zeros((self.K, count), dtype=np.float32, order="F")
+        check(self._lib.snmfnat_train_get_h(self._h, h.ctypes.data_as(C.POINTER(C.c_float)), int(t0), int(count)))
+        return h
+
+
+def basis_train_core(TF_pow, R: int, sample_idx, p: dict, *, h_init, device: int = 0, comm=None):
+    """Numeric core of run_basis_train.m:80-91,112-116 on the GPU: exemplar init B_init = TF_mag(:, idx) (:81-83),
+    sparse_nmf with W and H updated (:84-88), column normalisation + 1e-9 (:112-114).  `sample_idx` replaces
+    randsample, `h_init` is the rand(R, T) of sparse_nmf.m:134.  Returns (B, A, objective)."""
+    TF_pow = np.asarray(TF_pow)
+    F, T = TF_pow.shape
+    if str(p.get("cf", "kl")) != "kl":
+        raise SnmfnatError(-4, "the tensor-core training path implements cf='kl' (use sparse_nmf for other divergences)")
+    tr = Train(get_context(device), F, R, T, float(p["sparsity"]))
+    try:
+        tr.set_data(TF_pow, TF_pow[:, np.asarray(sample_idx)], h_init)
+        if p.get("cost_check", 1):
+            obj = tr.run(int(p["max_iter"]), float(p["conv_eps"]))
+        else:
+            tr.iterate(int(p["max_iter"]))
+            obj = dict(div=np.zeros(0), cost=np.zeros(0), iters=int(p["max_iter"]))
+        w = tr.get_w().astype(np.float64)
+        h = tr.get_h().astype(np.float64)
+    finally:
+        tr.close()
+    wn = np.sqrt(np.sum(w ** 2, axis=0))
+    return w / wn + 1e-9, h, obj

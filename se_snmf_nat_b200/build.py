@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lcufft", "-lnccl", "-lcudart"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lcufft", "-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
