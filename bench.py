@@ -377,6 +377,11 @@ def main():
     ap.add_argument("--utts", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="enhance", choices=["enhance", "train"],
+                    help="enhance = BASELINE.json's headline metric (default); train = configs[3] dictionary training")
+    ap.add_argument("--train-frames", type=int, default=1_250_000, help="frames (per GPU for weak scaling)")
+    ap.add_argument("--train-k", type=int, default=256)
+    ap.add_argument("--train-scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     args.warmup_ref = min(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -391,7 +396,11 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "train":
+            import bench_train
+            bench_train.run(args, rank, world, local_rank, ClockSampler, measured_peaks)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -623,6 +623,10 @@ class Train:
     def dev_ptr(self, which: str) -> int:
         return int(self._lib.snmfnat_train_dev_ptr(self._h, which.encode()) or 0)
 
+    def commit_v(self):
+        """After filling dev_ptr("V") in place: rebuild the bin-major copy of V."""
+        check(self._lib.snmfnat_train_commit_v(self._h))
+
     def reset(self):
         check(self._lib.snmfnat_train_reset(self._h))
 
