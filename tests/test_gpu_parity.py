@@ -123,3 +123,43 @@ def test_unsupported_configs_fail_loudly(api, bases, rng_inputs):
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+_VARIANT_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from se_snmf_nat_b200 import api
+from oracle import snmf_oracle as O
+g = {golden!r}
+bases = np.load(g + "/bases.npz"); wavs = np.load(g + "/wavs.npz"); rng = np.load(g + "/rng_seed1.npz")
+pcm = wavs["M03_in"][4000:4000 + 160 * 150]
+out, st = api.enhance_batch([pcm], api.default_p(), bases["B_DFT_x"], bases["B_DFT_d"], h_init=rng["h_init"],
+                            Ad_blk_init=rng["Ad_blk"], return_stats=True)
+tr = []
+ref, _ = O.enhance_utterance(pcm, O.default_params(), bases["B_DFT_x"], bases["B_DFT_d"], h_init=rng["h_init"],
+                             Ad_blk_init=rng["Ad_blk"], trace=tr)
+assert len(out[0]) == len(ref)
+d = int(np.abs(out[0].astype(int) - ref.astype(int)).max())
+assert d <= 1, d
+hi = sum(int(t["h_iters"]) for t in tr); wi = sum(int(t["w_iters"]) for t in tr)
+assert st["h_iters"] == hi, (st["h_iters"], hi)
+assert st["w_iters"] == wi, (st["w_iters"], wi)
+print("variant ok", d, st["h_iters"], st["w_iters"])
+"""
+
+
+@pytest.mark.parametrize("env", [dict(SNMFNAT_HSOLVE="reg"), dict(SNMFNAT_FORCE_GENERIC="1")],
+                         ids=["reg_hsolve", "generic_kernels"])
+def test_alternative_kernel_generations_agree_with_oracle(env):
+    """The older kernel generations stay selectable (SNMFNAT_HSOLVE=reg: register-resident H-solve; SNMFNAT_FORCE_GENERIC=1:
+    the any-geometry kernels) and must reproduce the oracle too.  The switches are read once per process."""
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLDEN, ROOT
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT.format(root=str(ROOT), golden=str(GOLDEN))], env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "variant ok" in r.stdout
