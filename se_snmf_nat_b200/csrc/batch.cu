@@ -2,6 +2,7 @@
 // one GPU.  STFT of every frame up front (batched cuFFT), then one {H-solve, gain, W-solve} kernel triple per
 // hop over all still-active utterances, then ISTFT + overlap-add of every frame.
 #include <algorithm>
+#include <array>
 #include <memory>
 #include <cstring>
 #include <numeric>
@@ -15,8 +16,12 @@ struct snmfnat_batch {
   int n_utt = 0;
   std::vector<int64_t> len, out_len, out_off_h, pcm_off_h;
   std::vector<int> n_hops_u;       // per utterance
-  std::vector<int> order;          // slot -> utterance (sorted by hops, longest first)
+  std::vector<int> order;          // slot -> first utterance of the slot's unit (units sorted by hops, longest first)
   std::vector<int> slot_of;        // utterance -> slot
+  int n_slots = 0;                 // units: single utterances, or chains of utterances (B_D_u.mat carry-over)
+  std::vector<int> events;         // chain boundaries {slot, utt, step0, n_hops}, sorted by step0
+  std::vector<int> ev_begin;       // ev_begin[g] .. ev_begin[g+1]: events of global step g
+  DevBuf<int> d_events, d_loff0, d_nhops0;
   std::vector<long long> frame_base_u;
   std::vector<int> active_at;      // active_at[g] = number of active slots at global step g
   int max_hops = 0;
@@ -59,7 +64,6 @@ int snmfnat_batch_create(snmfnat_ctx* ctx, const snmfnat_params* p, const double
   SN_API_BEGIN
   SN_REQUIRE(ctx && p && win_stft && win_istft && B_x && B_d && len && h_init && out, SNMFNAT_EINVAL, "NULL argument");
   SN_REQUIRE(n_utt > 0, SNMFNAT_EINVAL, "n_utt must be positive");
-  SN_REQUIRE(chain_id == nullptr, SNMFNAT_EUNSUPPORTED, "chain mode (B_D_u.mat carry-over) is not implemented yet");
   SN_REQUIRE(p->adapt_train_N == 0 || p->R_a == 0 || Ad_blk_init != nullptr, SNMFNAT_EINVAL,
              "Ad_blk_init is required when adaptation is on (init_buff.m:38 draws it with rand)");
   SN_CUDA(cudaSetDevice(ctx->device));
@@ -85,40 +89,86 @@ int snmfnat_batch_create(snmfnat_ctx* ctx, const snmfnat_params* p, const double
     oo += (b->out_len[u] + 7) / 8 * 8;
   }
   b->pcm_total = po; b->out_total = oo;
-  // slots: one per utterance, longest first, so the active set at any step is a prefix
-  b->order.resize(n_utt);
-  std::iota(b->order.begin(), b->order.end(), 0);
-  std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int q) { return b->n_hops_u[a] > b->n_hops_u[q]; });
+  // slots: one per unit (an utterance, or a chain of utterances that hand their adapted noise basis on through
+  // B_D_u.mat, src/NTF_sep_event_RT.m:28-38,136-139), longest first, so the active set at any step is a prefix
+  std::vector<std::vector<int>> units;
+  {
+    std::vector<std::pair<int, int>> seen;  // chain id -> unit
+    for (int u = 0; u < n_utt; ++u) {
+      const int cid = chain_id ? chain_id[u] : -1;
+      int at = -1;
+      if (cid >= 0)
+        for (auto& pr : seen)
+          if (pr.first == cid) at = pr.second;
+      if (at < 0) {
+        at = (int)units.size();
+        units.emplace_back();
+        if (cid >= 0) seen.emplace_back(cid, at);
+      }
+      units[at].push_back(u);
+    }
+  }
+  const int n_slots = (int)units.size();
+  b->n_slots = n_slots;
+  std::vector<long long> unit_hops(n_slots, 0);
+  for (int j = 0; j < n_slots; ++j)
+    for (int u : units[j]) unit_hops[j] += b->n_hops_u[u];
+  SN_REQUIRE(*std::max_element(unit_hops.begin(), unit_hops.end()) < (1ll << 30), SNMFNAT_EINVAL, "a chain is too long");
+  std::vector<int> uorder(n_slots);
+  std::iota(uorder.begin(), uorder.end(), 0);
+  std::stable_sort(uorder.begin(), uorder.end(), [&](int a, int q) { return unit_hops[a] > unit_hops[q]; });
+  b->order.resize(n_slots);
   b->slot_of.resize(n_utt);
   long long fb = 0;
-  std::vector<long long> fb_slot(n_utt);
-  std::vector<int> nh_slot(n_utt), loff(n_utt, 0);
-  for (int s = 0; s < n_utt; ++s) {
-    const int u = b->order[s];
-    b->slot_of[u] = s;
+  std::vector<long long> fb_slot(n_slots);
+  std::vector<int> nh_slot(n_slots), loff(n_slots, 0), total_slot(n_slots);
+  std::vector<std::array<int, 4>> evs;
+  for (int s = 0; s < n_slots; ++s) {
+    const std::vector<int>& mem = units[uorder[s]];
+    b->order[s] = mem[0];
     fb_slot[s] = fb;
-    b->frame_base_u[u] = fb;
-    nh_slot[s] = b->n_hops_u[u];
-    fb += b->n_hops_u[u];
+    nh_slot[s] = b->n_hops_u[mem[0]];
+    total_slot[s] = (int)unit_hops[uorder[s]];
+    int step = 0;
+    for (size_t j = 0; j < mem.size(); ++j) {
+      const int u = mem[j];
+      b->slot_of[u] = s;
+      b->frame_base_u[u] = fb;          // the frames of a chain are consecutive: frame = frame_base[slot] + step
+      if (j > 0) evs.push_back({s, u, step, b->n_hops_u[u]});
+      fb += b->n_hops_u[u];
+      step += b->n_hops_u[u];
+    }
   }
   b->NF = fb;
-  b->max_hops = nh_slot[0];
+  b->max_hops = total_slot[0];
   b->active_at.assign(b->max_hops, 0);
-  for (int g = 0, s = n_utt; g < b->max_hops; ++g) {
-    while (s > 0 && nh_slot[s - 1] <= g) --s;
+  for (int g = 0, s = n_slots; g < b->max_hops; ++g) {
+    while (s > 0 && total_slot[s - 1] <= g) --s;
     b->active_at[g] = s;
   }
+  std::stable_sort(evs.begin(), evs.end(), [](const std::array<int, 4>& a, const std::array<int, 4>& q) { return a[2] < q[2]; });
+  b->ev_begin.assign(b->max_hops + 1, 0);
+  for (auto& e : evs) {
+    b->events.insert(b->events.end(), e.begin(), e.end());
+    b->ev_begin[e[2] + 1]++;
+  }
+  for (int g = 0; g < b->max_hops; ++g) b->ev_begin[g + 1] += b->ev_begin[g];
   // device buffers
-  b->sb.alloc(n_utt, c.d);
+  b->sb.alloc(n_slots, c.d);
   b->sb.set_bases(ctx, B_x, B_d);
-  if (c.sc.adapt_train_N) b->sb.set_ad_init(ctx, Ad_blk_init, ad_stride, b->order);
+  if (c.sc.adapt_train_N) b->sb.set_ad_init(ctx, Ad_blk_init, ad_stride, n_utt, b->order);
   b->sb.win_stft.alloc(c.g.sz); b->sb.win_istft.alloc(c.g.sz);
   SN_CUDA(cudaMemcpy(b->sb.win_stft.p, win_stft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
   SN_CUDA(cudaMemcpy(b->sb.win_istft.p, win_istft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
   SN_CUDA(cudaMemcpy(b->sb.h_init.p, h_init, c.d.R * sizeof(double), cudaMemcpyHostToDevice));
-  SN_CUDA(cudaMemcpy(b->sb.l_offset.p, loff.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice));
-  SN_CUDA(cudaMemcpy(b->sb.n_hops.p, nh_slot.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice));
-  SN_CUDA(cudaMemcpy(b->sb.frame_base.p, fb_slot.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice));
+  b->d_loff0.alloc(n_slots); b->d_nhops0.alloc(n_slots);
+  SN_CUDA(cudaMemcpy(b->d_loff0.p, loff.data(), n_slots * sizeof(int), cudaMemcpyHostToDevice));
+  SN_CUDA(cudaMemcpy(b->d_nhops0.p, nh_slot.data(), n_slots * sizeof(int), cudaMemcpyHostToDevice));
+  SN_CUDA(cudaMemcpy(b->sb.frame_base.p, fb_slot.data(), n_slots * sizeof(long long), cudaMemcpyHostToDevice));
+  if (!b->events.empty()) {
+    b->d_events.alloc(b->events.size());
+    SN_CUDA(cudaMemcpy(b->d_events.p, b->events.data(), b->events.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   b->pcm.alloc((size_t)std::max<int64_t>(po, 8));
   b->out.alloc((size_t)std::max<int64_t>(oo, 8));
   b->d_pcm_off.alloc(n_utt); b->d_len.alloc(n_utt); b->d_frame_base_u.alloc(n_utt); b->d_out_off.alloc(n_utt);
@@ -218,6 +268,8 @@ int snmfnat_batch_run(snmfnat_batch* b) {
   };
   mark();  // 0: start
   b->sb.reset(ctx);
+  SN_CUDA(cudaMemcpyAsync(b->sb.l_offset.p, b->d_loff0.p, b->n_slots * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  SN_CUDA(cudaMemcpyAsync(b->sb.n_hops.p, b->d_nhops0.p, b->n_slots * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
   const UttTables ut = utt_tables(b);
   // STFT of every frame
   launch_frame_pcm(ctx, c.g, ut, b->pcm.p, b->sb.win_stft.p, b->frames.p);
@@ -231,6 +283,8 @@ int snmfnat_batch_run(snmfnat_batch* b) {
   const TraceArrays* trp = b->trace ? &tr : nullptr;
   for (int g = 0; g < b->max_hops; ++g) {
     const int na = b->active_at[g];
+    if (b->ev_begin[g + 1] > b->ev_begin[g])   // slots whose chain moves on to its next file at this step
+      b->sb.chain_boundary(ctx, b->d_events.p + 4 * (size_t)b->ev_begin[g], b->ev_begin[g + 1] - b->ev_begin[g]);
     launch_hsolve(ctx, c.d, c.sc, st, fr, b->sb.h_init.p, na, g);
     mark();
     launch_gain(ctx, c.d, c.sc, st, fr, trp, na, g);

@@ -63,7 +63,6 @@ void SlotBuffers::alloc(int S_, const OnlineDims& d_) {
   Bd0.alloc((size_t)S * d.R_d * LDF);
   Bd1.alloc((size_t)S * d.R_d * LDF);
   Ad_blk.alloc((size_t)S * d.m_a * d.R_a);
-  Ad_init.alloc((size_t)S * d.m_a * d.R_a);
   lam_blk.alloc((size_t)S * d.m_a * LDF);
   r_blk.alloc((size_t)S * d.P_len_l * LDF);
   lambda_dav.alloc((size_t)S * LDF);
@@ -88,21 +87,72 @@ void SlotBuffers::set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B
   upload_basis(ctx, B_d, d.F, d.R_d, d.LDF, Bd_fix.p);
 }
 
-void SlotBuffers::set_ad_init(snmfnat_ctx* ctx, const double* Ad_blk_init, int64_t stride,
-                              const std::vector<int>& order) {
+void SlotBuffers::set_ad_init(snmfnat_ctx* ctx, const double* Ad_blk_init, int64_t stride, int n_utt,
+                              const std::vector<int>& first_utt) {
   // MATLAB R_a x m_a column-major == [m_a][R_a] time-slot major: the ring layout, oldest column first
   const size_t per = (size_t)d.m_a * d.R_a;
   if (per == 0) return;
-  for (int s = 0; s < S; ++s) {
-    const double* src = Ad_blk_init + (stride ? (size_t)order[s] * stride : 0);
-    SN_CUDA(cudaMemcpyAsync(Ad_init.p + (size_t)s * per, src, per * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  n_utt_ad = n_utt;
+  Ad_init.alloc((size_t)n_utt * per);
+  if (stride == (int64_t)per) {
+    SN_CUDA(cudaMemcpyAsync(Ad_init.p, Ad_blk_init, (size_t)n_utt * per * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int u = 0; u < n_utt; ++u) {
+      const double* src = Ad_blk_init + (stride ? (size_t)u * stride : 0);
+      SN_CUDA(cudaMemcpyAsync(Ad_init.p + (size_t)u * per, src, per * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
   }
+  first_utt_dev.alloc(S);
+  SN_CUDA(cudaMemcpyAsync(first_utt_dev.p, first_utt.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   SN_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
+// Ad_blk of slot s <- Ad_init of utterance first_utt[s]
+__global__ void gather_ad_kernel(const double* __restrict__ ad_init, const int* __restrict__ first_utt, double* __restrict__ ad_blk,
+                                 size_t per, int S) {
+  const size_t total = per * (size_t)S;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = i / per;
+    ad_blk[i] = ad_init[(size_t)first_utt[s] * per + (i - s * per)];
+  }
+}
+// One block per event: re-run init_buff (src/init_buff.m:17-62) for the slot, keeping Bd / bd_sel.
+__global__ void chain_boundary_kernel(const int* __restrict__ ev, OnlineDims d, double* lam_blk, double* r_blk, double* lambda_dav,
+                                      double* Xm_tilde_prev, double* ad_blk, const double* __restrict__ ad_init, int* rblk_pos,
+                                      int* ring_head, int* update_switch, int* l_offset, int* n_hops) {
+  const int slot = ev[4 * blockIdx.x], utt = ev[4 * blockIdx.x + 1], step0 = ev[4 * blockIdx.x + 2], nh = ev[4 * blockIdx.x + 3];
+  const size_t LDF = d.LDF;
+  double* p = lam_blk + (size_t)slot * d.m_a * LDF;
+  for (size_t i = threadIdx.x; i < (size_t)d.m_a * LDF; i += blockDim.x) p[i] = 0.0;
+  p = r_blk + (size_t)slot * d.P_len_l * LDF;
+  for (size_t i = threadIdx.x; i < (size_t)d.P_len_l * LDF; i += blockDim.x) p[i] = 0.0;
+  for (size_t i = threadIdx.x; i < LDF; i += blockDim.x) {
+    lambda_dav[(size_t)slot * LDF + i] = 0.0;
+    Xm_tilde_prev[(size_t)slot * LDF + i] = 0.0;
+  }
+  const size_t per = (size_t)d.m_a * d.R_a;
+  for (size_t i = threadIdx.x; i < per; i += blockDim.x) ad_blk[(size_t)slot * per + i] = ad_init[(size_t)utt * per + i];
+  if (threadIdx.x == 0) {
+    rblk_pos[slot] = 0;
+    ring_head[slot] = 0;
+    update_switch[slot] = 1;   // init_buff.m:41
+    l_offset[slot] = step0;    // l restarts at 1
+    n_hops[slot] = nh;
+  }
+}
+
+void SlotBuffers::chain_boundary(snmfnat_ctx* ctx, const int* events_dev, int n_events) {
+  if (n_events <= 0) return;
+  chain_boundary_kernel<<<n_events, 512, 0, ctx->stream>>>(events_dev, d, lam_blk.p, r_blk.p, lambda_dav.p, Xm_tilde_prev.p,
+                                                            Ad_blk.p, Ad_init.p, rblk_pos.p, ring_head.p, update_switch.p,
+                                                            l_offset.p, n_hops.p);
+  count_launch(ctx);
+  check_launch(ctx, "chain_boundary_kernel");
+}
+
 __global__ void broadcast_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t per, int S) {
   const size_t total = per * (size_t)S;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -123,7 +173,10 @@ void SlotBuffers::reset(snmfnat_ctx* ctx) {
   broadcast_kernel<<<blocks, 256, 0, st>>>(Bd_fix.p, Bd0.p, per, S);
   broadcast_kernel<<<blocks, 256, 0, st>>>(Bd_fix.p, Bd1.p, per, S);  // columns >= R_a must be valid in both buffers
   count_launch(ctx, 2);
-  if (Ad_blk.n) SN_CUDA(cudaMemcpyAsync(Ad_blk.p, Ad_init.p, Ad_blk.n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (Ad_blk.n && Ad_init.n) {
+    gather_ad_kernel<<<blocks, 256, 0, st>>>(Ad_init.p, first_utt_dev.p, Ad_blk.p, (size_t)d.m_a * d.R_a, S);
+    count_launch(ctx);
+  }
   check_launch(ctx, "state reset");
 }
 

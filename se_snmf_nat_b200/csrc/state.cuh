@@ -21,15 +21,20 @@ struct SlotBuffers {
   DevBuf<double> Bx, Bd_fix, Bd0, Bd1, Ad_blk, Ad_init, lam_blk, r_blk, lambda_dav, Xm_tilde_prev;
   DevBuf<double> A, Xhat, Dhat, Q, G, h_cost, h_init, win_stft, win_istft;
   DevBuf<int> rblk_pos, bd_sel, ring_head, update_switch, h_iters, gated, do_update, n_up, idx_up, idx_rem, w_iters, err_flag;
-  DevBuf<int> l_offset, n_hops;
+  DevBuf<int> l_offset, n_hops, first_utt_dev;
+  int n_utt_ad = 0;   // utterances held in Ad_init
   DevBuf<long long> frame_base;
   DevBuf<unsigned long long> stats;
 
   void alloc(int S, const OnlineDims& d);
   // bases are host column-major F x R doubles
   void set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B_d);
-  // Ad_blk_init: R_a x m_a column-major per slot, `stride` doubles apart (0 = shared); order[s] = source index
-  void set_ad_init(snmfnat_ctx* ctx, const double* Ad_blk_init, int64_t stride, const std::vector<int>& order);
+  // Ad_blk_init: R_a x m_a column-major per UTTERANCE, `stride` doubles apart (0 = shared by all); first_utt[s] = the
+  // utterance slot s starts with (later members of a chain are installed by chain_boundary)
+  void set_ad_init(snmfnat_ctx* ctx, const double* Ad_blk_init, int64_t stride, int n_utt, const std::vector<int>& first_utt);
+  // A slot moves on to the next file of its chain (src/NTF_sep_event_RT.m:28-46: init_buff with the bases loaded from
+  // B_D_u.mat): everything of init_buff is reset EXCEPT the adapted noise basis; events = {slot, utt, step0, n_hops}
+  void chain_boundary(snmfnat_ctx* ctx, const int* events_dev, int n_events);
   // reset every slot to init_buff (src/init_buff.m:17-62): zero histories, Bd <- B_d, Ad_blk <- init
   void reset(snmfnat_ctx* ctx);
   SlotState view() const;

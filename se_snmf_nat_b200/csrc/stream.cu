@@ -88,7 +88,7 @@ int snmfnat_stream_create(snmfnat_ctx* ctx, const snmfnat_params* p, const doubl
   s->sb.set_bases(ctx, B_DFT_x, B_Mel_d ? B_Mel_d : B_DFT_d);
   (void)B_Mel_x;
   std::vector<int> order(1, 0);
-  if (c.sc.adapt_train_N) s->sb.set_ad_init(ctx, Ad_blk_init, 0, order);
+  if (c.sc.adapt_train_N) s->sb.set_ad_init(ctx, Ad_blk_init, 0, 1, order);
   s->sb.win_stft.alloc(c.g.sz); s->sb.win_istft.alloc(c.g.sz);
   SN_CUDA(cudaMemcpy(s->sb.win_stft.p, win_stft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
   SN_CUDA(cudaMemcpy(s->sb.win_istft.p, win_istft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));

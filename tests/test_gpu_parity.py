@@ -111,6 +111,41 @@ def test_settings_variants(api, O, bases, wavs, rng_inputs, variant):
     assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1
 
 
+def test_chain_mode_carries_the_noise_basis_between_files(api, O, bases, wavs, rng_inputs):
+    """Do_MultiBatch / NTF_sep_event_RT semantics (src/NTF_sep_event_RT.m:28-38,136-139): inside a target directory the
+    adapted noise basis of file i is the starting basis of file i+1 (B_D_u.mat); chains are independent of each other
+    and of the unchained utterances in the same batch."""
+    h_init, _ = rng_inputs
+    p = api.default_p()
+    po = O.default_params()
+    rs = np.random.RandomState(21)
+    m03, m04 = wavs["M03_in"], wavs["M04_in"]
+    pcms = [m03[2000:2000 + 160 * 70], m04[:160 * 45], m03[20000:20000 + 160 * 55 + 40], m04[30000:30000 + 160 * 80],
+            m03[40000:40000 + 160 * 30], np.zeros(0, np.int16), m04[50000:50000 + 160 * 25]]
+    chain = [0, 7, 0, 7, -1, 0, 7]          # chain 0: files 0,2,5 ; chain 7: files 1,3,6 ; file 4 alone
+    ads = np.stack([rs.rand(50, 100) for _ in pcms])
+    ctx = api.get_context(0)
+    b = api.Batch(ctx, p, bases["B_DFT_x"], bases["B_DFT_d"], [len(x) for x in pcms], h_init, ads, chain_id=chain)
+    b.upload(pcms)
+    b.run()
+    outs = b.download()
+    for members in ([0, 2, 5], [1, 3, 6], [4]):
+        ref, Bd = O.enhance_chain([pcms[i] for i in members], po, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init,
+                                  Ad_blk_inits=[ads[i] for i in members])
+        for i, r in zip(members, ref):
+            assert len(outs[i]) == len(r)
+            assert np.abs(outs[i].astype(int) - r.astype(int)).max() <= 1, i
+        assert rel_err(Bd, b.noise_basis(members[-1])) <= SPEC_TOL      # what the reference would leave in B_D_u.mat
+    # a second run of the same batch object starts every chain from the shipped basis again
+    b.run()
+    again = b.download()
+    assert all(np.array_equal(a, o) for a, o in zip(again, outs))
+    # chaining matters: file 2 enhanced on its own differs from file 2 as the second file of chain 0
+    alone = api.enhance_batch([pcms[2]], p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=ads[2])[0]
+    assert not np.array_equal(alone, outs[2])
+    b.close()
+
+
 def test_unsupported_configs_fail_loudly(api, bases, rng_inputs):
     h_init, Ad = rng_inputs
     for over in (dict(Splice=1), dict(blk_len_sep=2, blk_hop_sep=2)):
