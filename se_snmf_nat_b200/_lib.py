@@ -120,6 +120,7 @@ SIGNATURES = {
     "snmfnat_batch_enable_trace": (C.c_int, [_vp, C.c_int]),
     "snmfnat_batch_get_trace": (C.c_int, [_vp, C.c_int, C.c_char_p, _dp, C.c_int64]),
     "snmfnat_batch_set_profile": (C.c_int, [_vp, C.c_int]),
+    "snmfnat_batch_set_groups": (C.c_int, [_vp, C.c_int]),
     "snmfnat_batch_get_profile": (C.c_int, [_vp, _dp, _P(C.c_int64)]),
     "snmfnat_batch_get_noise_basis": (C.c_int, [_vp, C.c_int, _dp]),
     "snmfnat_enhance_batch": (C.c_int, [_vp, _P(Params), _dp, _dp, _dp, _dp, C.c_int, C.c_int, _i16pp,

@@ -233,6 +233,10 @@ class Batch:
     def download_packed(self, packed_ptr: int):
         check(self._lib.snmfnat_batch_download_packed(self._h, C.cast(packed_ptr, C.POINTER(C.c_int16))))
 
+    def set_groups(self, n: int):
+        """Scheduling only: n interleaved slot groups on separate CUDA streams (snmfnat_batch_set_groups)."""
+        check(self._lib.snmfnat_batch_set_groups(self._h, int(n)))
+
     def set_profile(self, on=True):
         check(self._lib.snmfnat_batch_set_profile(self._h, 1 if on else 0))
 

@@ -5,6 +5,7 @@
 #include <array>
 #include <memory>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include "state.cuh"
 
@@ -43,8 +44,16 @@ struct snmfnat_batch {
   std::vector<cudaEvent_t> ev;
   double prof_ms[6] = {0, 0, 0, 0, 0, 0};
   int64_t prof_cnt[6] = {0, 0, 0, 0, 0, 0};
+  // interleaved slot groups on their own CUDA streams (slot s belongs to group s % n_groups)
+  int n_groups = 1;
+  std::vector<cudaStream_t> gstream;
+  std::vector<cudaEvent_t> gdone;
+  cudaEvent_t fork_ev = nullptr;
   ~snmfnat_batch() {
     for (auto e : ev) cudaEventDestroy(e);
+    for (auto e : gdone) cudaEventDestroy(e);
+    for (auto st : gstream) cudaStreamDestroy(st);
+    if (fork_ev) cudaEventDestroy(fork_ev);
   }
 };
 
@@ -74,6 +83,10 @@ int snmfnat_batch_create(snmfnat_ctx* ctx, const snmfnat_params* p, const double
   SN_REQUIRE(hsolve_smem_bytes(c.d) <= (size_t)ctx->max_smem_optin, SNMFNAT_EUNSUPPORTED,
              "basis [B_x B_d] (%d x %d) does not fit the 4-CTA shared-memory H-solve", c.d.F, c.d.R);
   b->n_utt = n_utt;
+  if (const char* e = getenv("SNMFNAT_GROUPS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 16) b->n_groups = v;
+  }
   b->len.assign(len, len + n_utt);
   b->n_hops_u.resize(n_utt); b->out_len.resize(n_utt); b->pcm_off_h.resize(n_utt); b->out_off_h.resize(n_utt);
   b->frame_base_u.resize(n_utt);
@@ -281,17 +294,47 @@ int snmfnat_batch_run(snmfnat_batch* b) {
   FrameArrays fr{b->Ym.p, b->Xt.p};
   TraceArrays tr{b->trA.p, b->trQ.p, b->trG.p, b->trInfo.p};
   const TraceArrays* trp = b->trace ? &tr : nullptr;
+  const int NG = prof ? 1 : b->n_groups;   // the per-class event profile needs the launches serialised on one stream
+  if (NG > 1) {
+    while ((int)b->gstream.size() < NG) {
+      cudaStream_t q;
+      SN_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+      b->gstream.push_back(q);
+      cudaEvent_t e;
+      SN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      b->gdone.push_back(e);
+    }
+    if (!b->fork_ev) SN_CUDA(cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming));
+    SN_CUDA(cudaEventRecord(b->fork_ev, ctx->stream));
+    for (int q = 0; q < NG; ++q) SN_CUDA(cudaStreamWaitEvent(b->gstream[q], b->fork_ev, 0));
+  }
+  cudaStream_t main_stream = ctx->stream;
   for (int g = 0; g < b->max_hops; ++g) {
     const int na = b->active_at[g];
-    if (b->ev_begin[g + 1] > b->ev_begin[g])   // slots whose chain moves on to its next file at this step
-      b->sb.chain_boundary(ctx, b->d_events.p + 4 * (size_t)b->ev_begin[g], b->ev_begin[g + 1] - b->ev_begin[g]);
-    launch_hsolve(ctx, c.d, c.sc, st, fr, b->sb.h_init.p, na, g);
-    mark();
-    launch_gain(ctx, c.d, c.sc, st, fr, trp, na, g);
-    mark();
-    launch_wsolve(ctx, c.d, c.sc, st, trp, na, g);
-    mark();
+    for (int q = 0; q < NG; ++q) {
+      const int nq = na > q ? (na - q + NG - 1) / NG : 0;
+      if (NG > 1) ctx->stream = b->gstream[q];
+      // slots whose chain moves on to its next file at this step
+      for (int e = b->ev_begin[g]; e < b->ev_begin[g + 1]; ++e)
+        if (b->events[4 * (size_t)e] % NG == q) b->sb.chain_boundary(ctx, b->d_events.p + 4 * (size_t)e, 1);
+      if (nq == 0) continue;
+      OnlineDims dq = c.d;
+      dq.slot0 = q;
+      dq.slot_stride = NG;
+      launch_hsolve(ctx, dq, c.sc, st, fr, b->sb.h_init.p, nq, g);
+      mark();
+      launch_gain(ctx, dq, c.sc, st, fr, trp, nq, g);
+      mark();
+      launch_wsolve(ctx, dq, c.sc, st, trp, nq, g);
+      mark();
+    }
   }
+  ctx->stream = main_stream;
+  if (NG > 1)
+    for (int q = 0; q < NG; ++q) {
+      SN_CUDA(cudaEventRecord(b->gdone[q], b->gstream[q]));
+      SN_CUDA(cudaStreamWaitEvent(main_stream, b->gdone[q], 0));
+    }
   // ISTFT + overlap-add
   launch_istft_pre(ctx, c.g, b->Yc.p, b->Xt.p, b->NF);
   SN_CUFFT(cufftExecZ2D(b->fft.inv, reinterpret_cast<cufftDoubleComplex*>(b->Yc.p), b->frames.p));
@@ -367,6 +410,13 @@ int snmfnat_batch_get_stats(snmfnat_batch* b, snmfnat_batch_stats* out) {
   out->flops = (double)s[1] * (4.0 * F * R + 10.0 * F) + (double)s[2] * (4.0 * F * mean_rup * ma + 12.0 * F * ma) +
                (double)s[0] * 0.7e6;
   out->launches = b->launches_last;
+  SN_API_END
+}
+
+int snmfnat_batch_set_groups(snmfnat_batch* b, int n_groups) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && n_groups >= 1 && n_groups <= 16, SNMFNAT_EINVAL, "n_groups must be in 1..16");
+  b->n_groups = n_groups;
   SN_API_END
 }
 

@@ -13,6 +13,9 @@ struct OnlineDims {
   int F;      // n2 = fftlength/2+1 rows of the DFT-domain vectors
   int LDF;    // padded F
   int R_x, R_d, R, R_a, m_a, P_len_l;
+  // the slots a launch covers: slot0 + i * slot_stride, i = 0 .. n_active-1 (interleaved groups run on separate CUDA
+  // streams so that the tail of one group's kernel overlaps the next kernel of another group)
+  int slot0 = 0, slot_stride = 1;
 };
 
 // Scalars of p used inside the kernels.

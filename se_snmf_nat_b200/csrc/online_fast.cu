@@ -116,7 +116,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
                    int g_step) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int slot = blockIdx.x / HF_CL;
+  const int slot = d.slot0 + (int)(blockIdx.x / HF_CL) * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;  // uniform over the cluster
 
@@ -445,7 +445,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   constexpr int XN = LT::XN;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int slot = blockIdx.x / WF_CL;
+  const int slot = d.slot0 + (int)(blockIdx.x / WF_CL) * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;
   if (!st.do_update[slot]) return;  // uniform over the cluster

@@ -89,7 +89,7 @@ hsolve_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, cons
               int g_step) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int slot = blockIdx.x / HS_CL;
+  const int slot = d.slot0 + (int)(blockIdx.x / HS_CL) * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;  // uniform over the cluster
 
@@ -320,7 +320,7 @@ constexpr int GN_THREADS = 256;
 
 __global__ void __launch_bounds__(GN_THREADS)
 gain_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, TraceArrays tr, int has_trace, int g_step) {
-  const int slot = blockIdx.x;
+  const int slot = d.slot0 + (int)blockIdx.x * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;
   const int tid = threadIdx.x;
@@ -550,7 +550,7 @@ __global__ void __cluster_dims__(WS_CL, 1, 1) __launch_bounds__(WS_THREADS, 1)
 wsolve_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr, int has_trace, int g_step) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int slot = blockIdx.x / WS_CL;
+  const int slot = d.slot0 + (int)(blockIdx.x / WS_CL) * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;
   if (!st.do_update[slot]) return;  // uniform over the cluster

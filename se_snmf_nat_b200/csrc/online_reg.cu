@@ -93,7 +93,7 @@ hsolve_reg_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, 
   constexpr int KP = L::KP, HS = L::HS, XN = L::XN;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int slot = slot0 + blockIdx.x / HR_CL;
+  const int slot = d.slot0 + (int)(blockIdx.x / HR_CL) * d.slot_stride + slot0;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;  // uniform over the cluster
 

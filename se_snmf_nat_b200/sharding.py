@@ -64,7 +64,7 @@ def enhance_corpus(pcms: Sequence[np.ndarray], engine: Callable[[List[np.ndarray
                    *, rank: int = 0, world: int = 1, chain_id: Optional[Sequence[int]] = None, group=None,
                    gather_to: Optional[int] = 0):
     """Enhance a corpus on `world` ranks.  `engine(pcms_local, indices_local, chain_local)` enhances this rank's
-    utterances (on the GPU in production: `api.enhance_batch`; the tests inject the oracle) and returns their int16
+    utterances (on the GPU in production: `api.enhance_batch`; the tests inject a CPU checker) and returns their int16
     outputs in the same order.  With `gather_to` = r the full list (corpus order) is returned on rank r and None
     elsewhere; with gather_to=None every rank returns {index: output} of its own shard."""
     lengths = [len(x) for x in pcms]

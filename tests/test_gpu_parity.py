@@ -146,6 +146,31 @@ def test_chain_mode_carries_the_noise_basis_between_files(api, O, bases, wavs, r
     b.close()
 
 
+def test_stream_groups_do_not_change_results(api, bases, wavs, rng_inputs):
+    """snmfnat_batch_set_groups is a scheduling knob: interleaved slot groups on separate CUDA streams give bit-identical
+    output (also with chains, whose boundary re-initialisation has to run on the owning group's stream)."""
+    h_init, _ = rng_inputs
+    p = api.default_p()
+    rs = np.random.RandomState(3)
+    m04 = wavs["M04_in"]
+    pcms = [m04[o:o + n] for o, n in [(0, 160 * 40), (7000, 160 * 33 + 5), (15000, 160 * 52), (26000, 160 * 18),
+                                       (31000, 160 * 47), (40000, 160 * 29), (47000, 160 * 36)]]
+    chain = [0, -1, 0, 1, -1, 1, 0]
+    ads = np.stack([rs.rand(50, 100) for _ in pcms])
+    ctx = api.get_context(0)
+    res = {}
+    for ng in (1, 3):
+        b = api.Batch(ctx, p, bases["B_DFT_x"], bases["B_DFT_d"], [len(x) for x in pcms], h_init, ads, chain_id=chain)
+        b.set_groups(ng)
+        b.upload(pcms)
+        b.run()
+        res[ng] = (b.download(), b.stats())
+        b.close()
+    assert all(np.array_equal(a, c) for a, c in zip(res[1][0], res[3][0]))
+    for k in ("hops", "h_iters", "w_iters", "w_solves"):
+        assert res[1][1][k] == res[3][1][k]
+
+
 def test_unsupported_configs_fail_loudly(api, bases, rng_inputs):
     h_init, Ad = rng_inputs
     for over in (dict(Splice=1), dict(blk_len_sep=2, blk_hop_sep=2)):
