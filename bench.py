@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--utts", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--groups", type=int, default=int(os.environ.get("SNMFNAT_GROUPS", "1")),
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("SNMFNAT_GROUPS", "3")),
                     help="interleaved slot groups on separate CUDA streams (scheduling only)")
     ap.add_argument("--workload", default="enhance", choices=["enhance", "train"],
                     help="enhance = BASELINE.json's headline metric (default); train = configs[3] dictionary training")

@@ -197,7 +197,7 @@ int snmfnat_batch_run(snmfnat_batch* b);
  * ((floor(len/frameshift)+1)*frameshift, filewise_run_IS16.m:146,162-165). */
 /* Scheduling knob, no effect on results: the slots are split into n_groups interleaved groups whose per-hop kernels
  * run on separate CUDA streams, so that the tail of one group's kernel overlaps the next kernel of another group.
- * Default 1 (or the SNMFNAT_GROUPS environment variable). */
+ * Default 3 (or the SNMFNAT_GROUPS environment variable). */
 int snmfnat_batch_set_groups(snmfnat_batch* b, int n_groups);
 int snmfnat_batch_download(snmfnat_batch* b, int16_t* const* out);
 int snmfnat_batch_download_packed(snmfnat_batch* b, int16_t* out_packed);

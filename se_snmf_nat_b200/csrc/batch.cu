@@ -45,7 +45,7 @@ struct snmfnat_batch {
   double prof_ms[6] = {0, 0, 0, 0, 0, 0};
   int64_t prof_cnt[6] = {0, 0, 0, 0, 0, 0};
   // interleaved slot groups on their own CUDA streams (slot s belongs to group s % n_groups)
-  int n_groups = 1;
+  int n_groups = 3;
   std::vector<cudaStream_t> gstream;
   std::vector<cudaEvent_t> gdone;
   cudaEvent_t fork_ev = nullptr;

@@ -86,29 +86,61 @@ constexpr int HF_CL = 4;
 constexpr int HF_ROWS = 128;   // rows per CTA
 constexpr int HF_KG = 8;       // k groups in the lambda pass
 
+constexpr int HF_HP = 34;      // stride of the per-k-group copy of h (>= ceil(R/8), even)
 struct HfLayout {
   int E, XN;
-  size_t off_W, off_Wt, off_v, off_r, off_lam, off_h, off_dph, off_wn, off_xch, off_misc, bytes;
+  size_t off_W, off_Wt, off_v, off_r, off_lam, off_h, off_hp, off_dph, off_recv, off_misc, off_bar, bytes;
 };
 __host__ __device__ inline HfLayout hf_layout(int F, int R) {
   HfLayout L;
   L.E = F - HF_CL * HF_ROWS;
-  L.XN = R + 8;
+  L.XN = R + 2;
   size_t o = 0;
   L.off_W = o;    o += (size_t)R * HF_ROWS;
   L.off_Wt = o;   o += (size_t)(L.E > 0 ? L.E : 0) * R;
   o = (o + 1) & ~(size_t)1;
   L.off_v = o;    o += HF_ROWS + 8;
   L.off_r = o;    o += HF_ROWS + 8;
-  L.off_lam = o;  o += (size_t)HF_KG * HF_ROWS;
+  L.off_lam = o;  o += (size_t)(HF_KG / 2) * HF_ROWS;   // 4 partial groups: the two k groups of a warp are added by shuffle
   L.off_h = o;    o += R;
-  L.off_dph = o;  o += R;
-  L.off_wn = o;   o += R;
   o = (o + 1) & ~(size_t)1;
-  L.off_xch = o;  o += 2 * (size_t)L.XN;
+  L.off_hp = o;   o += (size_t)HF_KG * HF_HP;
+  L.off_dph = o;  o += R;
+  o = (o + 1) & ~(size_t)1;
+  // [2][4][XN]: pushed partials of g, [R] cost partial, [R+1] sum(h).  Its head doubles as the [2][XN] buffer of the
+  // one-off normalisation exchange before the loop.
+  L.off_recv = o; o += 2 * (size_t)HF_CL * L.XN;
   L.off_misc = o; o += 48;
+  L.off_bar = o;  o += 2;                          // 2 mbarriers
   L.bytes = o * sizeof(double);
   return L;
+}
+
+// mbarrier + st.async (push over distributed shared memory, completion counted in bytes on the receiver's barrier)
+__device__ __forceinline__ unsigned hf_mapa(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void hf_st_async(unsigned raddr, double v, unsigned rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               :: "r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void hf_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hf_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hf_mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
 }
 
 __global__ void __cluster_dims__(HF_CL, 1, 1) __launch_bounds__(HF_THREADS, 1)
@@ -134,10 +166,17 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
   double* r_s = smem + L.off_r;       // ratio v./lambda
   double* lam_part = smem + L.off_lam;
   double* h_s = smem + L.off_h;
+  double* hp_s = smem + L.off_hp;     // [8][HF_HP]: h of the atoms k = kg + 8 j, grouped by kg (lambda pass reads pairs)
   double* dph_s = smem + L.off_dph;
-  double* wn_s = smem + L.off_wn;
-  double* xch = smem + L.off_xch;     // [2][R + 8]: g partial, [R] = cost partial
+  double* xch = smem + L.off_recv;    // [2][XN] of the normalisation exchange (aliases the head of recv; see below)
+  double* recv = smem + L.off_recv;   // [2][4][XN] partials pushed by the 4 CTAs of the cluster
   double* misc = smem + L.off_misc;   // [0..7] cost partials per warp, [8] hsum, [16..23] lambda of tail rows
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem + L.off_bar);
+  if (tid == 0) {
+    hf_mbar_init(bar0, 1);
+    hf_mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   const double* __restrict__ W1 = st.Bx;
   const double* __restrict__ W2 = st.Bd[st.bd_sel[slot]] + (size_t)slot * d.R_d * LDF;
@@ -176,6 +215,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
   cluster.sync();
 
   // ---- column norms, h scaling (sparse_nmf.m:157-160), denominators (:192-193) ----
+  double wn_r = 1.0, dph_r = 0.0;   // of atom `tid`
   if (tid < R) {
     double s2 = 0.0, s1 = 0.0;
     for (int c = 0; c < HF_CL; ++c) {
@@ -184,59 +224,70 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
       s1 += rx[L.XN + tid];
     }
     const double wn = sqrt(s2);
-    wn_s[tid] = wn;
-    dph_s[tid] = 1.0 / fmax(s1 / wn + sc.sparsity, flr);   // reciprocal of the H-update denominator (:192-193)
+    wn_r = wn;
+    dph_s[tid] = 1.0 / wn;                                  // staging of 1/wn for the scaling loop below
+    dph_r = 1.0 / fmax(s1 / wn + sc.sparsity, flr);         // reciprocal of the H-update denominator (:192-193)
     h_s[tid] = h_init[tid] * wn;
+    hp_s[(tid & 7) * HF_HP + (tid >> 3)] = h_s[tid];
   }
   cluster.sync();  // everyone has read both exchange buffers before they are reused; publishes wn_s / h_s
   for (int k = warp; k < R; k += HF_WARPS) {
-    const double wn = wn_s[k];
+    const double inv = dph_s[k];        // one division per column (above); the elements are scaled by the reciprocal
 #pragma unroll
     for (int j = 0; j < HF_ROWS / 32; ++j) {
       double* p = Ws + (size_t)k * HF_ROWS + lane + 32 * j;
-      *p = *p / wn;
+      *p = *p * inv;
     }
-    if (tail_rank && lane < E) Wt[(size_t)lane * R + k] = Wt[(size_t)lane * R + k] / wn;
+    if (tail_rank && lane < E) Wt[(size_t)lane * R + k] = Wt[(size_t)lane * R + k] * inv;
   }
   __syncthreads();
 
   // ---- multiplicative updates ----
-  const int kg = warp & (HF_KG - 1), rh = warp >> 3;   // lambda pass: k group, row half
+  // lambda pass roles: warp = (pair of k groups kp / kp+4, 32-row quarter rq); the half-warps take one k group each
+  const int kp = warp & 3, rq = warp >> 2, half = lane >> 4, l16 = lane & 15;
+  const int kg = kp + 4 * half;
   const int kb = warp;                                  // g pass: block of 16 atoms, lanes 16..31 take rows 64..127
   const int kl = lane & 15, fh = lane >> 4;
   const int kB = kb * 16 + kl;
+  // lambda partials of W x for the vector staged in hp_s (grouped by k & 7) / h_s: every lane sums the columns
+  // k = kg, kg+8, ... for the row pair rq*32 + 2*l16 + {0,1} (one 16-byte load per column; the x of two consecutive
+  // columns of the group comes as one pair); the two half-warps are added by shuffle -> 4 partial groups per row
+  auto lambda_pass = [&]() {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    const double* base = Ws + rq * 32 + ((2 * l16) ^ (kg << 1));   // k & 7 == kg for every column of this group
+    const double* hp = hp_s + kg * HF_HP;
+    int k = kg, j = 0;
+    for (; k + 8 < R; k += 16, j += 2) {
+      const double2 hh = *reinterpret_cast<const double2*>(hp + j);
+      const double2 w0 = *reinterpret_cast<const double2*>(base + (size_t)k * HF_ROWS);
+      const double2 w1 = *reinterpret_cast<const double2*>(base + (size_t)(k + 8) * HF_ROWS);
+      a0 = fma(w0.x, hh.x, a0);
+      a1 = fma(w0.y, hh.x, a1);
+      b0 = fma(w1.x, hh.y, b0);
+      b1 = fma(w1.y, hh.y, b1);
+    }
+    if (k < R) {
+      const double h0 = hp[j];
+      const double2 w0 = *reinterpret_cast<const double2*>(base + (size_t)k * HF_ROWS);
+      a0 = fma(w0.x, h0, a0);
+      a1 = fma(w0.y, h0, a1);
+    }
+    a0 += b0;
+    a1 += b1;
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+    if (half == 0) *reinterpret_cast<double2*>(lam_part + kp * HF_ROWS + rq * 32 + 2 * l16) = make_double2(a0, a1);
+    if (tail_rank && warp < E) {  // tail row `warp`: lanes over atoms
+      double s = 0.0;
+      for (int kk = lane; kk < R; kk += 32) s = fma(Wt[(size_t)warp * R + kk], h_s[kk], s);
+      s = warp_sum(s);
+      if (lane == 0) misc[16 + warp] = s;
+    }
+  };
   int it = 0, buf = 0;
   double last_cost = INFINITY, cost = 0.0;
   for (;;) {
-    // (A) lambda partials: this warp sums columns k = kg, kg+8, ... for rows rh*64 + lane + {0,32}
-    {
-      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-      const double* base = Ws + rh * 64 + (lane ^ (kg << 1));   // k & 7 == kg for every column of this group
-      int k = kg;
-      for (; k + 8 < R; k += 16) {
-        const double h0 = h_s[k], h1 = h_s[k + 8];
-        const double* w0 = base + (size_t)k * HF_ROWS;
-        const double* w1 = base + (size_t)(k + 8) * HF_ROWS;
-        a0 = fma(w0[0], h0, a0);
-        a1 = fma(w0[32], h0, a1);
-        b0 = fma(w1[0], h1, b0);
-        b1 = fma(w1[32], h1, b1);
-      }
-      if (k < R) {
-        const double h0 = h_s[k];
-        const double* w0 = base + (size_t)k * HF_ROWS;
-        a0 = fma(w0[0], h0, a0);
-        a1 = fma(w0[32], h0, a1);
-      }
-      lam_part[kg * HF_ROWS + rh * 64 + lane] = a0 + b0;
-      lam_part[kg * HF_ROWS + rh * 64 + lane + 32] = a1 + b1;
-      if (tail_rank && warp < E) {  // tail row `warp`: lanes over atoms
-        double s = 0.0;
-        for (int kk = lane; kk < R; kk += 32) s = fma(Wt[(size_t)warp * R + kk], h_s[kk], s);
-        s = warp_sum(s);
-        if (lane == 0) misc[16 + warp] = s;
-      }
-    }
+    lambda_pass();   // (A)
     __syncthreads();
     // (R) ratio + cost terms for the CTA's rows (threads 0..127) and the tail rows (threads 128..128+E)
     if (warp < 5) {
@@ -246,7 +297,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
         double lam = 0.0;
         if (main_row) {
 #pragma unroll
-          for (int q = 0; q < HF_KG; ++q) lam += lam_part[q * HF_ROWS + tid];
+          for (int q = 0; q < HF_KG / 2; ++q) lam += lam_part[q * HF_ROWS + tid];
         } else {
           lam = misc[16 + tid - HF_ROWS];
         }
@@ -257,8 +308,14 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
       }
     }
     __syncthreads();
-    // (B) g partial over this CTA's rows: lane <-> atom kB, half-warps split the rows, pairs of rows per step
-    double* xb = xch + (size_t)buf * L.XN;
+    // (B) g partial over this CTA's rows: lane <-> atom kB, half-warps split the rows, pairs of rows per step.  Every
+    //     partial is PUSHED to the 4 CTAs of the cluster by the lane that produced it (st.async; the receiver's
+    //     mbarrier counts the bytes): no cluster barrier, no fence, no remote loads on the critical path.
+    const unsigned bar = bar0 + 8u * (unsigned)buf;
+    const unsigned parity = (unsigned)(it >> 1) & 1u;
+    double* rb = recv + (size_t)buf * HF_CL * L.XN;
+    const unsigned my_row = (unsigned)__cvta_generic_to_shared(rb + (size_t)rank * L.XN);
+    if (tid == 0) hf_mbar_expect_tx(bar, (unsigned)((HF_CL * (R + 1) + 1) * sizeof(double)));
     if (kb * 16 < R) {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       if (kB < R) {
@@ -283,13 +340,15 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
       if (fh == 0 && kB < R) {
         if (tail_rank)
           for (int e = 0; e < E; ++e) g = fma(Wt[(size_t)e * R + kB], r_s[HF_ROWS + e], g);
-        xb[kB] = g;
+        const unsigned la = my_row + 8u * (unsigned)kB;
+#pragma unroll
+        for (int c = 0; c < HF_CL; ++c) hf_st_async(hf_mapa(la, c), g, hf_mapa(bar, c));
       }
     } else if (warp == HF_WARPS - 1) {
-      double s = 0.0;  // sum of h for the sparsity term of the cost (identical order on every CTA)
+      double s = 0.0;  // sum of h for the sparsity term of the cost (identical order on every CTA); stays in this CTA
       for (int kk = lane; kk < R; kk += 32) s += h_s[kk];
       s = warp_sum(s);
-      if (lane == 0) misc[8] = s;
+      if (lane == 0) hf_st_async(hf_mapa(my_row + 8u * (unsigned)(R + 1), rank), s, hf_mapa(bar, rank));
     } else if (warp == HF_WARPS - 2) {
       double cterm = 0.0;  // KL divergence terms of this CTA's rows                  sparse_nmf.m:250
       if (sc.cost_check && it >= 1) {
@@ -305,18 +364,22 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
         }
       }
       cterm = warp_sum(cterm);
-      if (lane == 0) xb[R] = cterm;
+      if (lane == 0) {
+        const unsigned la = my_row + 8u * (unsigned)R;
+#pragma unroll
+        for (int c = 0; c < HF_CL; ++c) hf_st_async(hf_mapa(la, c), cterm, hf_mapa(bar, c));
+      }
     }
-    cluster.sync();
+    hf_mbar_wait(bar, parity);
     // (C) combine the 4 CTAs in rank order, convergence test, h update
     double gk = 0.0;
     if (tid < R)
-      for (int c = 0; c < HF_CL; ++c) gk += cluster.map_shared_rank(xb, c)[tid];
+      for (int c = 0; c < HF_CL; ++c) gk += rb[(size_t)c * L.XN + tid];
     bool stop = false;
     if (sc.cost_check && it >= 1) {
       double div = 0.0;
-      for (int c = 0; c < HF_CL; ++c) div += cluster.map_shared_rank(xb, c)[R];
-      cost = div + sc.sparsity * misc[8];                                // :261
+      for (int c = 0; c < HF_CL; ++c) div += rb[(size_t)c * L.XN + R];
+      cost = div + sc.sparsity * rb[(size_t)rank * L.XN + R + 1];          // :261
       if (it > 1 && sc.conv_eps > 0.0) {
         const double e = fabs(cost - last_cost) / last_cost;             // :274
         if (e < sc.conv_eps) stop = true;
@@ -325,7 +388,11 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     }
     if (it >= sc.max_iter) stop = true;
     if (stop) break;
-    if (tid < R) h_s[tid] = h_s[tid] * gk * dph_s[tid];                   // :195
+    if (tid < R) {
+      const double hn = h_s[tid] * gk * dph_r;                             // :195
+      h_s[tid] = hn;
+      hp_s[(tid & 7) * HF_HP + (tid >> 3)] = hn;
+    }
     __syncthreads();
     buf ^= 1;
     ++it;
@@ -333,43 +400,35 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
 
   // ---- outputs ----
   __syncthreads();
+  double h_fin = 0.0;
   if (tid < R) {
-    if (rank == 0) st.A[(size_t)slot * R + tid] = h_s[tid];
-    dph_s[tid] = h_s[tid] * wn_s[tid];   // activations for the un-normalised basis (bnmf_sep_event_RT_IS16.m:174,197)
+    h_fin = h_s[tid];
+    if (rank == 0) st.A[(size_t)slot * R + tid] = h_fin;
   }
   if (rank == 0 && tid == 0) {
     st.h_iters[slot] = it;
     st.h_cost[slot] = cost;
   }
-  __syncthreads();
   for (int part = 0; part < 2; ++part) {
-    const int k_lo = part == 0 ? 0 : R1, k_hi = part == 0 ? R1 : R;
-    double a0 = 0.0, a1 = 0.0;
-    for (int k = k_lo + kg; k < k_hi; k += HF_KG) {
-      const double hk = dph_s[k];
-      const double* w0 = Ws + (size_t)k * HF_ROWS + rh * 64 + (lane ^ ((k & 7) << 1));
-      a0 = fma(w0[0], hk, a0);
-      a1 = fma(w0[32], hk, a1);
+    __syncthreads();
+    if (tid < R) {
+      // activations for the un-normalised basis (bnmf_sep_event_RT_IS16.m:174,197), restricted to the class
+      const double x = ((tid < R1) == (part == 0)) ? h_fin * wn_r : 0.0;
+      h_s[tid] = x;
+      hp_s[(tid & 7) * HF_HP + (tid >> 3)] = x;
     }
-    lam_part[kg * HF_ROWS + rh * 64 + lane] = a0;
-    lam_part[kg * HF_ROWS + rh * 64 + lane + 32] = a1;
-    if (tail_rank && warp < E) {
-      double s = 0.0;
-      for (int kk = k_lo + lane; kk < k_hi; kk += 32) s = fma(Wt[(size_t)warp * R + kk], dph_s[kk], s);
-      s = warp_sum(s);
-      if (lane == 0) misc[16 + warp] = s;
-    }
+    __syncthreads();
+    lambda_pass();
     __syncthreads();
     double* dst = (part == 0 ? st.Xhat : st.Dhat) + (size_t)slot * LDF;
     if (tid < HF_ROWS) {
       double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < HF_KG; ++q) s += lam_part[q * HF_ROWS + tid];
+      for (int q = 0; q < HF_KG / 2; ++q) s += lam_part[q * HF_ROWS + tid];
       dst[f0 + tid] = s;
     } else if (tail_rank && tid < HF_ROWS + E) {
       dst[HF_CL * HF_ROWS + tid - HF_ROWS] = misc[16 + tid - HF_ROWS];
     }
-    __syncthreads();
   }
   cluster.sync();  // nobody may exit while a peer can still read its exchange buffers
 }

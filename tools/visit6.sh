@@ -1,0 +1,12 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_parity.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_parity.log
+tail -15 gpurun_out/pytest_parity.log
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v5.log 2>&1
+python - <<PY
+import json
+l=[x for x in open("gpurun_out/bench_v5.log") if x.startswith("{")]
+d=json.loads(l[-1]); print("xRT", round(d["value"],1), "ms", round(d["ms_per_step"],1), "e2e", round(d["e2e"]["value"],1))
+for k,v in d["roofline_all"].items(): print(k, {a:(round(b,3) if isinstance(b,float) else b) for a,b in v.items() if a in ("ms_per_step","frac","achieved")})
+PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hsolve_fast -s 60 -c 1 -f -o gpurun_out/hsolve_fast_v5 python tools/prof_run.py 148 2.0 > gpurun_out/prof_h5.log 2>&1
