@@ -145,7 +145,7 @@ __device__ __forceinline__ void hf_mbar_wait(unsigned bar, unsigned parity) {
 
 __global__ void __cluster_dims__(HF_CL, 1, 1) __launch_bounds__(HF_THREADS, 1)
 hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, const double* __restrict__ h_init,
-                   int g_step) {
+                   int g_step, const double2* __restrict__ log_tab) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int slot = d.slot0 + (int)(blockIdx.x / HF_CL) * d.slot_stride;
@@ -257,6 +257,7 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     const double* base = Ws + rq * 32 + ((2 * l16) ^ (kg << 1));   // k & 7 == kg for every column of this group
     const double* hp = hp_s + kg * HF_HP;
     int k = kg, j = 0;
+#pragma unroll 4
     for (; k + 8 < R; k += 16, j += 2) {
       const double2 hh = *reinterpret_cast<const double2*>(hp + j);
       const double2 w0 = *reinterpret_cast<const double2*>(base + (size_t)k * HF_ROWS);
@@ -356,11 +357,11 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
         for (int j = 0; j < HF_ROWS / 32; ++j) {
           const int f = lane + 32 * j;
           const double v = v_s[f], lam = lam_part[f];
-          cterm += v * log(r_s[f]) - v + lam;
+          cterm += fma(v, fast_log(r_s[f], log_tab), lam - v);
         }
         if (tail_rank && lane < E) {
           const double v = v_s[HF_ROWS + lane], lam = misc[16 + lane];
-          cterm += v * log(r_s[HF_ROWS + lane]) - v + lam;
+          cterm += fma(v, fast_log(r_s[HF_ROWS + lane], log_tab), lam - v);
         }
       }
       cterm = warp_sum(cterm);
@@ -444,7 +445,8 @@ void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScala
                         const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
   const HfLayout L = hf_layout(d.F, d.R);
   SN_CUDA(cudaFuncSetAttribute(hsolve_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-  hsolve_fast_kernel<<<dim3(HF_CL * n_active), dim3(HF_THREADS), L.bytes, ctx->stream>>>(d, sc, st, fr, h_init, g_step);
+  hsolve_fast_kernel<<<dim3(HF_CL * n_active), dim3(HF_THREADS), L.bytes, ctx->stream>>>(d, sc, st, fr, h_init, g_step,
+                                                                                         log_table(ctx));
   count_launch(ctx);
   check_launch(ctx, "hsolve_fast_kernel");
 }
@@ -462,7 +464,7 @@ struct WfLayout {
   static constexpr int KMAX = KT * 8;
   static constexpr int XN = 3 * KMAX + 8;
   int NP, HSd, VS, VROWS;
-  size_t off_H, off_V, off_red, off_xch, off_hs, off_wn, off_tot, off_tab, off_scratch, bytes;
+  size_t off_H, off_V, off_red, off_recv, off_hs, off_wn, off_tot, off_tab, off_scratch, off_bar, bytes;
   __host__ __device__ WfLayout(int m_a) {
     NP = (m_a + 15) / 16 * 16;
     HSd = NP + ((2 - NP % 8) + 8) % 8;          // == 2 (mod 8): conflict-free fragment loads in both GEMMs
@@ -472,13 +474,14 @@ struct WfLayout {
     off_H = o;       o += (size_t)KMAX * HSd;
     off_V = o;       o += (size_t)NP * VS;
     off_red = o;     o += (size_t)2 * WF_WARPS * KMAX;
-    off_xch = o;     o += (size_t)2 * XN;
+    off_recv = o;    o += (size_t)2 * WF_CL * XN;   // [2][4][XN] partials pushed by the 4 CTAs
     off_hs = o;      o += KMAX;
     off_wn = o;      o += KMAX;
     off_tot = o;     o += 2 * KMAX;
     o = (o + 1) & ~(size_t)1;
     off_tab = o;     o += 256;
     off_scratch = o; o += 64;
+    off_bar = o;     o += 2;                        // 2 mbarriers
     bytes = o * sizeof(double);
   }
 };
@@ -520,7 +523,13 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   double* Hs = smem + L.off_H;
   double* Vs = smem + L.off_V;        // [NP][VS]: V slice of this CTA, pad = floor
   double* red = smem + L.off_red;     // [2][WF_WARPS][KMAX]
-  double* xch = smem + L.off_xch;     // [2][XN]
+  double* recv = smem + L.off_recv;   // [2][4][XN]
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem + L.off_bar);
+  if (tid == 0) {
+    hf_mbar_init(bar0, 1);
+    hf_mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   double* hs_s = smem + L.off_hs;
   double* wn_s = smem + L.off_wn;
   double* tot = smem + L.off_tot;     // [2][KMAX]
@@ -589,42 +598,56 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         if (g == 0) rw[8 * j + 2 * tg + e] = s;
       }
   };
-  // CTA partial (fixed warp order) -> exchange buffer; cluster barrier; totals in rank order -> tot[which][k]
-  auto cluster_combine = [&](int nwhich, int xbuf, bool with_cost, double* extra_out) {
+  // CTA partial (fixed warp order) PUSHED to the 4 CTAs of the cluster (st.async, bytes counted on the receiver's
+  // mbarrier: no cluster barrier / fence); totals in rank order -> tot[which][k]
+  unsigned rnd = 0;
+  auto cluster_combine = [&](int nwhich, bool with_cost, double* extra_out, bool inv_sqrt = false) {
     __syncthreads();
-    double* xb = xch + (size_t)xbuf * XN;
-    for (int i = tid; i < nwhich * KMAX; i += WF_THREADS) {
-      const int which = i / KMAX, k = i - which * KMAX;
+    const unsigned buf = rnd & 1u, parity = (rnd >> 1) & 1u;
+    const unsigned bar = bar0 + 8u * buf;
+    double* rb = recv + (size_t)buf * WF_CL * XN;
+    const int npay = nwhich * KMAX;
+    const unsigned my_row = (unsigned)__cvta_generic_to_shared(rb + (size_t)rank * XN);
+    if (tid == 0) hf_mbar_expect_tx(bar, (unsigned)(WF_CL * (npay + 1) * sizeof(double)));
+    if (tid < npay) {
+      const int which = tid / KMAX, k = tid - which * KMAX;
       double s = 0.0;
 #pragma unroll
       for (int ww = 0; ww < WF_WARPS; ++ww) s += red[((size_t)which * WF_WARPS + ww) * KMAX + k];
-      xb[i] = s;
+      const unsigned la = my_row + 8u * (unsigned)tid;
+#pragma unroll
+      for (int c = 0; c < WF_CL; ++c) hf_st_async(hf_mapa(la, c), s, hf_mapa(bar, c));
+    } else if (tid == WF_THREADS - 1) {  // per-warp cost partials, fixed order
+      double s = 0.0;
+      if (with_cost) {
+#pragma unroll
+        for (int ww = 0; ww < WF_WARPS; ++ww) s += scratch[ww];
+      }
+      const unsigned la = my_row + 8u * (unsigned)(3 * KMAX);
+#pragma unroll
+      for (int c = 0; c < WF_CL; ++c) hf_st_async(hf_mapa(la, c), s, hf_mapa(bar, c));
     }
-    if (with_cost && tid == WF_THREADS - 1) {  // per-warp cost partials, fixed order
+    hf_mbar_wait(bar, parity);
+    if (tid < npay) {
       double s = 0.0;
 #pragma unroll
-      for (int ww = 0; ww < WF_WARPS; ++ww) s += scratch[ww];
-      xb[3 * KMAX] = s;
-    }
-    cluster.sync();
-    for (int i = tid; i < nwhich * KMAX; i += WF_THREADS) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < WF_CL; ++c) s += cluster.map_shared_rank(xb, c)[i];
-      tot[i] = s;
+      for (int c = 0; c < WF_CL; ++c) s += rb[(size_t)c * XN + tid];
+      tot[tid] = inv_sqrt ? 1.0 / sqrt(s) : s;   // one sqrt + division per column instead of one per element
     }
     if (extra_out) {
       double s = 0.0;
 #pragma unroll
-      for (int c = 0; c < WF_CL; ++c) s += cluster.map_shared_rank(xb, c)[3 * KMAX];
+      for (int c = 0; c < WF_CL; ++c) s += rb[(size_t)c * XN + 3 * KMAX];
       *extra_out = s;
     }
+    ++rnd;
     __syncthreads();
   };
+  cluster.sync();  // the mbarriers of every CTA are initialised before anybody pushes
 
   // column norms of init_w (sparse_nmf.m:158)
   warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
-  cluster_combine(1, 1, false, nullptr);
+  cluster_combine(1, false, nullptr);
   if (tid < KMAX) wn_s[tid] = (tid < Ru) ? sqrt(tot[tid]) : 1.0;
   __syncthreads();
 #pragma unroll
@@ -660,7 +683,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   for (;;) {
     double cacc = 0.0;
     const bool want_cost = sc.cost_check && it >= 1;
-    for (int tgp = 0; tgp < ngroups; ++tgp) {
+    for (int tgp = 0; tgp < (tile_valid ? ngroups : 0); ++tgp) {   // a warp without a tile only takes part in the reductions
       const int n0 = tgp * 16;
       // GEMM 1: lambda tile = W * H for 16 history columns (even columns -> c0, odd -> c1)
       double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
@@ -716,7 +739,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
     cacc = warp_sum(cacc);
     if (lane == 0) scratch[warp] = cacc;
     double div = 0.0;
-    cluster_combine(2, 0, true, &div);
+    cluster_combine(2, true, &div);
     bool stop = false;
     if (want_cost) {
       cost = div + sc.sparsity * hsum_all;                                               // :261
@@ -738,18 +761,18 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         const double hs = hs_s[k];
         const double dpw = fmax(hs + tot[KMAX + k] * wv, flr);
         const double dmw = gacc[j][e] + (hs * tot[k]) * wv;
-        w[j][e] = (k < Ru) ? wv * dmw / dpw : 0.0;
+        w[j][e] = (k < Ru) ? wv * dmw * fast_rcp(dpw) : 0.0;
         gacc[j][e] = 0.0;
       }
     // column normalisation                                                              :242
     warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
-    cluster_combine(1, 1, false, nullptr);
+    cluster_combine(1, false, nullptr, true);
 #pragma unroll
     for (int j = 0; j < KT; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int k = 8 * j + 2 * tg + e;
-        if (k < Ru) w[j][e] = w[j][e] / sqrt(tot[k]);
+        if (k < Ru) w[j][e] = w[j][e] * tot[k];
       }
     ++it;
   }

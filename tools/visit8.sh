@@ -9,4 +9,3 @@ l=[x for x in open("gpurun_out/bench_v5.log") if x.startswith("{")]
 d=json.loads(l[-1]); print("xRT", round(d["value"],1), "ms", round(d["ms_per_step"],1), "e2e", round(d["e2e"]["value"],1))
 for k,v in d["roofline_all"].items(): print(k, {a:(round(b,3) if isinstance(b,float) else b) for a,b in v.items() if a in ("ms_per_step","frac","achieved")})
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wsolve_fast -s 60 -c 1 -f -o gpurun_out/wsolve_fast_v5 python tools/prof_run.py 148 2.0 > gpurun_out/prof_w5.log 2>&1
