@@ -147,7 +147,7 @@ class Batch:
     the hop loop of filewise_run_IS16.m:86-169 for every utterance."""
 
     def __init__(self, ctx: Context, p: dict, B_x, B_d, lengths: Sequence[int], h_init, Ad_blk_init,
-                 chain_id: Optional[Sequence[int]] = None):
+                 chain_id: Optional[Sequence[int]] = None, B_Mel_x=None, B_Mel_d=None, melmat=None):
         self.ctx = ctx
         self._lib = ctx._lib
         self.p = p
@@ -192,6 +192,22 @@ class Batch:
             _dptr(h_init), _dptr(ad), stride, C.byref(h)))
         self._h = h
         self._ps = ps
+        self.n1 = 0
+        if ps.B_sep_mode == _lib.SEP_MEL:   # filewise_run_IS16.m:46-51: the Mel slots take B_Mel_sub
+            if B_Mel_x is None or B_Mel_d is None:
+                raise ValueError("B_sep_mode='Mel' needs B_Mel_x and B_Mel_d")
+            bmx, bmd = _f64(B_Mel_x), _f64(B_Mel_d)
+            if bmd.shape[1] < ps.R_d:
+                bmd = _f64(np.concatenate([bmd, bmd[:, :ps.R_d - bmd.shape[1]]], axis=1))
+            if bmx.shape != (bmd.shape[0], ps.R_x) or bmd.shape[1] != ps.R_d:
+                raise ValueError("Mel basis shapes do not match p.R_x / p.R_d")
+            mm = None
+            if melmat is not None:
+                mm = _f64(melmat)
+                if mm.shape != (B_x.shape[0], bmx.shape[0]):
+                    raise ValueError("melmat must be n2 x n1 (what mel_matrix.m returns)")
+            check(self._lib.snmfnat_batch_set_mel(h, _dptr(bmx), _dptr(bmd), bmx.shape[0], _dptr(mm)))
+            self.n1 = bmx.shape[0]
         self.out_lengths = np.array([self._lib.snmfnat_batch_out_len(h, u) for u in range(self.n_utt)], dtype=np.int64)
         self.total_hops = int(self._lib.snmfnat_batch_total_hops(h))
 
@@ -262,18 +278,27 @@ class Batch:
         return buf if width > 1 else buf[:, 0]
 
     def noise_basis(self, u: int) -> np.ndarray:
-        F = self._ps.fftlength // 2 + 1
+        F = self.n1 if self.n1 else self._ps.fftlength // 2 + 1   # Mel mode adapts B_Mel_d
         out = np.empty((F, self._ps.R_d), dtype=np.float64, order="F")
         check(self._lib.snmfnat_batch_get_noise_basis(self._h, int(u), _dptr(out)))
         return out
 
 
+def mel_matrix(fs: int, NbCh: int, Nfft: int, warp: float = 1.0, fhigh: Optional[float] = None) -> np.ndarray:
+    """M = mel_matrix(fs,NbCh,Nfft,warp,fhigh), src/mel_matrix.m:9-38 (dense (Nfft/2+1) x NbCh)."""
+    M = np.zeros((Nfft // 2 + 1, NbCh), dtype=np.float64, order="F")
+    check(_lib.load().snmfnat_mel_matrix(int(fs), int(NbCh), int(Nfft), float(warp),
+                                         float(fhigh if fhigh is not None else -1.0), _dptr(M)))
+    return M
+
+
 def enhance_batch(pcms: Sequence[np.ndarray], p: dict, B_x, B_d, *, h_init, Ad_blk_init, device: int = 0,
-                  chain_id=None, return_stats=False):
+                  chain_id=None, return_stats=False, B_Mel_x=None, B_Mel_d=None, melmat=None):
     """Enhance a list of int16 signals (samples after the 44-byte WAV header) exactly like running
     filewise_run_IS16.m on each of them; returns the int16 outputs."""
     ctx = get_context(device)
-    b = Batch(ctx, p, B_x, B_d, [len(x) for x in pcms], h_init, Ad_blk_init, chain_id)
+    b = Batch(ctx, p, B_x, B_d, [len(x) for x in pcms], h_init, Ad_blk_init, chain_id, B_Mel_x=B_Mel_x, B_Mel_d=B_Mel_d,
+              melmat=melmat)
     try:
         b.upload(pcms)
         b.run()

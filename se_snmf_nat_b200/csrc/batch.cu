@@ -33,6 +33,7 @@ struct snmfnat_batch {
   DevBuf<long long> d_pcm_off, d_len, d_frame_base_u, d_out_off;
   DevBuf<int> d_n_hops_u;
   DevBuf<double> frames, Ym, Xt;
+  DevBuf<double> Ysep;             // Mel mode: the separation input of every frame [NF][LD1]
   DevBuf<double2> Yc;
   DevBuf<double> trA, trQ, trG;
   DevBuf<int> trInfo;
@@ -288,12 +289,23 @@ int snmfnat_batch_run(snmfnat_batch* b) {
   launch_frame_pcm(ctx, c.g, ut, b->pcm.p, b->sb.win_stft.p, b->frames.p);
   SN_CUFFT(cufftExecD2Z(b->fft.fwd, b->frames.p, reinterpret_cast<cufftDoubleComplex*>(b->Yc.p)));
   launch_stft_post(ctx, c.g, b->Yc.p, b->NF, b->Ym.p, nullptr);
+  const bool mel = c.sc.mel_mode != 0;
+  if (mel) {
+    SN_REQUIRE(b->sb.mel(), SNMFNAT_EINVAL, "B_sep_mode='Mel': call snmfnat_batch_set_mel before snmfnat_batch_run");
+    launch_mel_project(ctx, b->sb.melM.p, b->sb.n1, b->sb.LD1, c.d.F, c.d.LDF, b->Ym.p, b->NF, b->Ysep.p);
+  }
   mark();  // 1: STFT done
   // hop loop
   const SlotState st = b->sb.view();
   FrameArrays fr{b->Ym.p, b->Xt.p};
   TraceArrays tr{b->trA.p, b->trQ.p, b->trG.p, b->trInfo.p};
   const TraceArrays* trp = b->trace ? &tr : nullptr;
+  SlotState st_mel{};
+  FrameArrays fr_mel{nullptr, nullptr};
+  if (mel) {
+    st_mel = b->sb.view_mel();
+    fr_mel = FrameArrays{b->Ysep.p, nullptr};
+  }
   const int NG = prof ? 1 : b->n_groups;   // the per-class event profile needs the launches serialised on one stream
   if (NG > 1) {
     while ((int)b->gstream.size() < NG) {
@@ -321,12 +333,30 @@ int snmfnat_batch_run(snmfnat_batch* b) {
       OnlineDims dq = c.d;
       dq.slot0 = q;
       dq.slot_stride = NG;
-      launch_hsolve(ctx, dq, c.sc, st, fr, b->sb.h_init.p, nq, g);
-      mark();
-      launch_gain(ctx, dq, c.sc, st, fr, trp, nq, g);
-      mark();
-      launch_wsolve(ctx, dq, c.sc, st, trp, nq, g);
-      mark();
+      if (!mel) {
+        launch_hsolve(ctx, dq, c.sc, st, fr, b->sb.h_init.p, nq, g);
+        mark();
+        launch_gain(ctx, dq, c.sc, st, fr, trp, nq, g);
+        mark();
+        launch_wsolve(ctx, dq, c.sc, st, trp, nq, g);
+        mark();
+      } else {
+        // the two solves run on the Mel-sized view of the state (n1 bands); gain, block sparsity and the gate stay in
+        // the DFT domain (bnmf_sep_event_RT_IS16.m:107-119,165-211,295-319)
+        OnlineDims dm = b->sb.dims_mel();
+        dm.slot0 = q;
+        dm.slot_stride = NG;
+        launch_hsolve(ctx, dm, c.sc, st_mel, fr_mel, b->sb.h_init.p, nq, g);
+        mark();
+        launch_mel_post(ctx, dq, st, b->sb.melM.p, b->sb.n1, b->sb.LD1, b->sb.XhatM.p, b->sb.DhatM.p, b->Ysep.p, nq, g);
+        launch_gain(ctx, dq, c.sc, st, fr, trp, nq, g);
+        mark();
+        if (c.sc.adapt_train_N) {
+          launch_mel_hist(ctx, dq, st, b->sb.melM.p, b->sb.n1, b->sb.LD1, b->sb.lam_blk_mel.p, nq, g);
+          launch_wsolve(ctx, dm, c.sc, st_mel, trp, nq, g);
+        }
+        mark();
+      }
     }
   }
   ctx->stream = main_stream;
@@ -410,6 +440,25 @@ int snmfnat_batch_get_stats(snmfnat_batch* b, snmfnat_batch_stats* out) {
   out->flops = (double)s[1] * (4.0 * F * R + 10.0 * F) + (double)s[2] * (4.0 * F * mean_rup * ma + 12.0 * F * ma) +
                (double)s[0] * 0.7e6;
   out->launches = b->launches_last;
+  SN_API_END
+}
+
+int snmfnat_batch_set_mel(snmfnat_batch* b, const double* B_Mel_x, const double* B_Mel_d, int n1, const double* melmat) {
+  SN_API_BEGIN
+  SN_REQUIRE(b && B_Mel_x && B_Mel_d && n1 > 0, SNMFNAT_EINVAL, "bad argument");
+  SN_REQUIRE(b->cfg.sc.mel_mode, SNMFNAT_EINVAL, "the batch was not created with B_sep_mode='Mel'");
+  SN_REQUIRE(n1 <= 256, SNMFNAT_EUNSUPPORTED, "Mel mode supports up to 256 bands (got %d)", n1);
+  SN_CUDA(cudaSetDevice(b->ctx->device));
+  const Config& c = b->cfg;
+  std::vector<double> M;
+  if (!melmat) {  // init_buff.m:60-62: g.melmat = mel_matrix(p.fs, p.F_order, p.fftlength, 1, p.fs/2)'
+    SN_REQUIRE(c.p.F_order == n1, SNMFNAT_EINVAL, "B_Mel has %d rows but p.F_order = %d", n1, c.p.F_order);
+    M.resize((size_t)c.d.F * n1);
+    mel_matrix_host(c.p.fs, n1, c.p.fftlength, 1.0, c.p.fs / 2.0, M.data());
+    melmat = M.data();
+  }
+  b->sb.set_mel(b->ctx, n1, B_Mel_x, B_Mel_d, melmat);
+  b->Ysep.alloc((size_t)std::max<long long>(b->NF, 1) * b->sb.LD1);
   SN_API_END
 }
 
@@ -506,6 +555,11 @@ int snmfnat_batch_get_noise_basis(snmfnat_batch* b, int u, double* B_d) {
   const int s = b->slot_of[u];
   int sel = 0;
   SN_CUDA(cudaMemcpy(&sel, b->sb.bd_sel.p + s, sizeof(int), cudaMemcpyDeviceToHost));
+  if (c.sc.mel_mode && b->sb.mel()) {  // the adapted basis is B_Mel_d (n1 x R_d)
+    const double* srcm = (sel ? b->sb.BdM1.p : b->sb.BdM0.p) + (size_t)s * c.d.R_d * b->sb.LD1;
+    download_basis(b->ctx, srcm, b->sb.n1, c.d.R_d, b->sb.LD1, B_d);
+    return SNMFNAT_OK;
+  }
   const double* src = (sel ? b->sb.Bd1.p : b->sb.Bd0.p) + (size_t)s * c.d.R_d * c.d.LDF;
   download_basis(b->ctx, src, c.d.F, c.d.R_d, c.d.LDF, B_d);
   SN_API_END

@@ -27,6 +27,7 @@ struct OnlineScalars {
   double alpha_p, alpha_eta, alpha_d, beta, beta_max, Ar_up;
   int enhance_method;
   int update_period;     // floor(p.overlap_m_a * p.m_a), bnmf_sep_event_RT_IS16.m:293
+  int mel_mode;          // B_sep_mode = 'Mel': lambda_dav of the first hop comes from the Mel -> DFT image (:205-211,223-225)
 };
 
 // Pointers into the per-slot state arrays (slot-major).
@@ -103,6 +104,14 @@ void launch_hsolve_reg(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalar
 bool wsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d);
 void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                         const TraceArrays* tr, int n_active, int g_step);
+// Mel separation mode (mel.cu); M is the filterbank [n1][LDF] (band-major)
+void mel_matrix_host(int fs, int NbCh, int Nfft, double warp, double fhigh, double* M);
+void launch_mel_project(snmfnat_ctx* ctx, const double* M, int n1, int LD1, int F, int LDF, const double* Ym, long long NF,
+                        double* Ysep);
+void launch_mel_post(snmfnat_ctx* ctx, const OnlineDims& d, const SlotState& st, const double* M, int n1, int LD1,
+                     const double* XhatM, const double* DhatM, const double* Ysep, int n_active, int g_step);
+void launch_mel_hist(snmfnat_ctx* ctx, const OnlineDims& d, const SlotState& st, const double* M, int n1, int LD1,
+                     double* lam_blk_mel, int n_active, int g_step);
 // SNMFNAT_FORCE_GENERIC=1 in the environment disables the fast paths (used by the parity tests)
 bool force_generic();
 // SNMFNAT_HSOLVE=reg selects the experimental register-resident H-solve (online_reg.cu) instead of the shared-memory

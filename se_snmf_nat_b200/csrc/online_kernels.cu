@@ -376,7 +376,7 @@ gain_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, TraceA
   double* xprev = st.Xm_tilde_prev + (size_t)slot * LDF;
   for (int f = tid; f < F; f += GN_THREADS) {
     const double ym = Ym[f];
-    double ld = (l == 1) ? ym : ldav[f];
+    double ld = (l == 1 && !sc.mel_mode) ? ym : ldav[f];   // Mel mode: mel_post_kernel seeded it (:205-211)
     ld = sc.alpha_d * ld + (1.0 - sc.alpha_d) * Dh[f] * beta;
     double G;
     if (sc.enhance_method == SNMFNAT_ENH_WIENER) {

@@ -13,7 +13,9 @@ void make_config(snmfnat_ctx* ctx, const snmfnat_params& p, int n2, Config& cfg)
              SNMFNAT_EINVAL, "bad frame geometry");
   SN_REQUIRE(n2 == p.fftlength / 2 + 1, SNMFNAT_EINVAL, "basis has %d rows, expected fftlength/2+1 = %d", n2,
              p.fftlength / 2 + 1);
-  SN_REQUIRE(p.B_sep_mode == SNMFNAT_SEP_DFT, SNMFNAT_EUNSUPPORTED, "B_sep_mode='Mel' is not implemented yet");
+  SN_REQUIRE(p.B_sep_mode == SNMFNAT_SEP_DFT || p.B_sep_mode == SNMFNAT_SEP_MEL, SNMFNAT_EINVAL, "bad B_sep_mode");
+  SN_REQUIRE(p.B_sep_mode == SNMFNAT_SEP_DFT || p.MelConv == 1, SNMFNAT_EUNSUPPORTED,
+             "B_sep_mode='Mel' is implemented for MelConv=1 (Mel -> DFT conversion of the separated spectra, :165-172)");
   SN_REQUIRE(p.cf == SNMFNAT_CF_KL, SNMFNAT_EUNSUPPORTED, "online path implements cf='kl' only");
   SN_REQUIRE(p.basis_update_N == 0 && p.basis_update_E == 0, SNMFNAT_EUNSUPPORTED,
              "basis_update_N/E (W-update inside the separation solve) is not implemented");
@@ -36,6 +38,7 @@ void make_config(snmfnat_ctx* ctx, const snmfnat_params& p, int n2, Config& cfg)
   s.alpha_p = p.alpha_p; s.alpha_eta = p.alpha_eta; s.alpha_d = p.alpha_d; s.beta = p.beta; s.beta_max = p.beta_max;
   s.Ar_up = p.Ar_up; s.enhance_method = p.ENHANCE_METHOD;
   s.update_period = (int)std::floor(p.overlap_m_a * (double)p.m_a);  // bnmf_sep_event_RT_IS16.m:293
+  s.mel_mode = p.B_sep_mode == SNMFNAT_SEP_MEL;
   StftGeom& g = cfg.g;
   g.sz = p.framelength; g.shift = p.frameshift; g.fftlen = p.fftlength; g.half = n2; g.LDF = d.LDF; g.delay = p.delay;
   g.preemph = p.preemph; g.pow_ = p.pow; g.flr = p.nonzerofloor; g.overlapscale = p.overlapscale;
@@ -87,6 +90,40 @@ void SlotBuffers::set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B
   upload_basis(ctx, B_d, d.F, d.R_d, d.LDF, Bd_fix.p);
 }
 
+void SlotBuffers::set_mel(snmfnat_ctx* ctx, int n1_, const double* B_Mel_x, const double* B_Mel_d, const double* melmat) {
+  n1 = n1_;
+  LD1 = pad_ld(n1);
+  const size_t L1 = LD1;
+  melM.alloc((size_t)n1 * d.LDF);
+  BxM.alloc((size_t)d.R_x * L1);
+  BdM_fix.alloc((size_t)d.R_d * L1);
+  BdM0.alloc((size_t)S * d.R_d * L1);
+  BdM1.alloc((size_t)S * d.R_d * L1);
+  lam_blk_mel.alloc((size_t)S * d.m_a * L1);
+  XhatM.alloc((size_t)S * L1);
+  DhatM.alloc((size_t)S * L1);
+  upload_basis(ctx, melmat, d.F, n1, d.LDF, melM.p);      // column b of melmat (n2 long) -> row b of M
+  upload_basis(ctx, B_Mel_x, n1, d.R_x, LD1, BxM.p);
+  upload_basis(ctx, B_Mel_d, n1, d.R_d, LD1, BdM_fix.p);
+}
+
+OnlineDims SlotBuffers::dims_mel() const {
+  OnlineDims m = d;
+  m.F = n1;
+  m.LDF = LD1;
+  return m;
+}
+
+SlotState SlotBuffers::view_mel() const {
+  SlotState v = view();
+  v.Bx = BxM.p;
+  v.Bd_fix = BdM_fix.p;
+  v.Bd[0] = BdM0.p; v.Bd[1] = BdM1.p;
+  v.lam_blk = lam_blk_mel.p;
+  v.Xhat = XhatM.p; v.Dhat = DhatM.p;
+  return v;
+}
+
 void SlotBuffers::set_ad_init(snmfnat_ctx* ctx, const double* Ad_blk_init, int64_t stride, int n_utt,
                               const std::vector<int>& first_utt) {
   // MATLAB R_a x m_a column-major == [m_a][R_a] time-slot major: the ring layout, oldest column first
@@ -120,13 +157,17 @@ __global__ void gather_ad_kernel(const double* __restrict__ ad_init, const int* 
   }
 }
 // One block per event: re-run init_buff (src/init_buff.m:17-62) for the slot, keeping Bd / bd_sel.
-__global__ void chain_boundary_kernel(const int* __restrict__ ev, OnlineDims d, double* lam_blk, double* r_blk, double* lambda_dav,
+__global__ void chain_boundary_kernel(const int* __restrict__ ev, OnlineDims d, double* lam_blk_mel, int LD1, double* lam_blk, double* r_blk, double* lambda_dav,
                                       double* Xm_tilde_prev, double* ad_blk, const double* __restrict__ ad_init, int* rblk_pos,
                                       int* ring_head, int* update_switch, int* l_offset, int* n_hops) {
   const int slot = ev[4 * blockIdx.x], utt = ev[4 * blockIdx.x + 1], step0 = ev[4 * blockIdx.x + 2], nh = ev[4 * blockIdx.x + 3];
   const size_t LDF = d.LDF;
   double* p = lam_blk + (size_t)slot * d.m_a * LDF;
   for (size_t i = threadIdx.x; i < (size_t)d.m_a * LDF; i += blockDim.x) p[i] = 0.0;
+  if (lam_blk_mel) {
+    p = lam_blk_mel + (size_t)slot * d.m_a * LD1;
+    for (size_t i = threadIdx.x; i < (size_t)d.m_a * LD1; i += blockDim.x) p[i] = 0.0;
+  }
   p = r_blk + (size_t)slot * d.P_len_l * LDF;
   for (size_t i = threadIdx.x; i < (size_t)d.P_len_l * LDF; i += blockDim.x) p[i] = 0.0;
   for (size_t i = threadIdx.x; i < LDF; i += blockDim.x) {
@@ -146,7 +187,7 @@ __global__ void chain_boundary_kernel(const int* __restrict__ ev, OnlineDims d, 
 
 void SlotBuffers::chain_boundary(snmfnat_ctx* ctx, const int* events_dev, int n_events) {
   if (n_events <= 0) return;
-  chain_boundary_kernel<<<n_events, 512, 0, ctx->stream>>>(events_dev, d, lam_blk.p, r_blk.p, lambda_dav.p, Xm_tilde_prev.p,
+  chain_boundary_kernel<<<n_events, 512, 0, ctx->stream>>>(events_dev, d, mel() ? lam_blk_mel.p : nullptr, LD1, lam_blk.p, r_blk.p, lambda_dav.p, Xm_tilde_prev.p,
                                                             Ad_blk.p, Ad_init.p, rblk_pos.p, ring_head.p, update_switch.p,
                                                             l_offset.p, n_hops.p);
   count_launch(ctx);
@@ -173,6 +214,15 @@ void SlotBuffers::reset(snmfnat_ctx* ctx) {
   broadcast_kernel<<<blocks, 256, 0, st>>>(Bd_fix.p, Bd0.p, per, S);
   broadcast_kernel<<<blocks, 256, 0, st>>>(Bd_fix.p, Bd1.p, per, S);  // columns >= R_a must be valid in both buffers
   count_launch(ctx, 2);
+  if (mel()) {
+    const size_t perm = (size_t)d.R_d * LD1;
+    int bm = (int)((perm * S + 255) / 256);
+    if (bm > ctx->sm_count * 16) bm = ctx->sm_count * 16;
+    broadcast_kernel<<<bm, 256, 0, st>>>(BdM_fix.p, BdM0.p, perm, S);
+    broadcast_kernel<<<bm, 256, 0, st>>>(BdM_fix.p, BdM1.p, perm, S);
+    count_launch(ctx, 2);
+    lam_blk_mel.zero(st); XhatM.zero(st); DhatM.zero(st);
+  }
   if (Ad_blk.n && Ad_init.n) {
     gather_ad_kernel<<<blocks, 256, 0, st>>>(Ad_init.p, first_utt_dev.p, Ad_blk.p, (size_t)d.m_a * d.R_a, S);
     count_launch(ctx);

@@ -26,6 +26,15 @@ struct SlotBuffers {
   DevBuf<long long> frame_base;
   DevBuf<unsigned long long> stats;
 
+  // Mel separation mode: Mel-sized bases / history / reconstructions next to the DFT-domain state
+  int n1 = 0, LD1 = 0;
+  DevBuf<double> melM, BxM, BdM_fix, BdM0, BdM1, lam_blk_mel, XhatM, DhatM;
+  bool mel() const { return n1 > 0; }
+  // B_Mel_x n1 x R_x, B_Mel_d n1 x R_d, melmat n2 x n1 (host column-major, i.e. the matrix mel_matrix.m returns)
+  void set_mel(snmfnat_ctx* ctx, int n1, const double* B_Mel_x, const double* B_Mel_d, const double* melmat);
+  OnlineDims dims_mel() const;
+  SlotState view_mel() const;
+
   void alloc(int S, const OnlineDims& d);
   // bases are host column-major F x R doubles
   void set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B_d);

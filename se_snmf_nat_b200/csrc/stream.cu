@@ -82,6 +82,8 @@ int snmfnat_stream_create(snmfnat_ctx* ctx, const snmfnat_params* p, const doubl
   s->ctx = ctx;
   make_config(ctx, *p, n2, s->cfg);
   const Config& c = s->cfg;
+  SN_REQUIRE(!c.sc.mel_mode, SNMFNAT_EUNSUPPORTED,
+             "B_sep_mode='Mel' is available through the batch entry (snmfnat_batch_set_mel), not the per-hop stream entry");
   SN_REQUIRE(n1 == n2, SNMFNAT_EUNSUPPORTED, "DFT mode expects the Mel slots to hold the DFT bases (n1 == n2)");
   s->sb.alloc(1, c.d);
   // B_DFT_d is the adaptable basis; the "B_Mel_d" slot supplies the never-updated columns (:328 [sic])

@@ -241,12 +241,25 @@ hphase_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ 
       const bool row_ok = (t0 + row) < a.T;
       const float* vcol = a.Vt + t0 + row;
       float cost_tile = 0.f;
+      // V of this group's NEXT chunk is fetched while the current one is processed (the loads are the long pole of the
+      // epilogue otherwise: one DRAM round trip per chunk with nothing else in flight)
+      float vn[NC];
+      auto load_v = [&](int c, float (&dst)[NC]) {
+        const int f0 = c * NC;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) dst[j] = (row_ok && f0 + j < a.F) ? __ldg(vcol + (size_t)(f0 + j) * a.ldt) : 0.f;
+      };
+      {
+        const int c_first = ((int)(n & 1) == e) ? 0 : 1;
+        if (c_first < nch) load_v(c_first, vn);
+      }
       for (int c = 0; c < nch; ++c, ++n) {
         if ((int)(n & 1) != e) continue;
         const int f0 = c * NC;
         float v[NC];
 #pragma unroll
-        for (int j = 0; j < NC; ++j) v[j] = (row_ok && f0 + j < a.F) ? __ldg(vcol + (size_t)(f0 + j) * a.ldt) : 0.f;
+        for (int j = 0; j < NC; ++j) v[j] = vn[j];
+        if (c + 2 < nch) load_v(c + 2, vn);
         mbar_wait(lam_full + e, (n >> 1) & 1);
         tc_fence_after();
         uint32_t lam[NC];
@@ -487,11 +500,19 @@ wphase_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ 
     const int f = chunk * BM + row;
     const bool f_ok = f < a.F;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    float vn[NC];
+    auto load_v = [&](int i, float (&dst)[NC]) {
+      const long long t0 = (long long)(grp + i * a.ngroups) * NC;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) dst[j] = (f_ok && t0 + j < a.T) ? __ldg(a.V + (size_t)(t0 + j) * a.ldv + f) : 0.f;
+    };
+    if (e < n_my) load_v(e, vn);
     for (int i = e; i < n_my; i += 2) {
       const long long t0 = (long long)(grp + i * a.ngroups) * NC;
       float v[NC];
 #pragma unroll
-      for (int j = 0; j < NC; ++j) v[j] = (f_ok && t0 + j < a.T) ? __ldg(a.V + (size_t)(t0 + j) * a.ldv + f) : 0.f;
+      for (int j = 0; j < NC; ++j) v[j] = vn[j];
+      if (i + 2 < n_my) load_v(i + 2, vn);   // next stage of this group, in flight while this one is processed
       mbar_wait(lam_full + e, (i >> 1) & 1);
       tc_fence_after();
       uint32_t lam[NC];

@@ -71,3 +71,17 @@ def test_mex_gateways_compile_against_shim():
     r = subprocess.run(["make", "-C", str(ROOT / "mex"), "check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all gateways compile" in r.stdout
+
+
+def test_mel_matrix_matches_the_oracle():
+    """snmfnat_mel_matrix (src/mel_matrix.m) is host code of the library: checked here without a GPU."""
+    import numpy as np
+    from se_snmf_nat_b200 import api
+    from oracle import snmf_oracle as O
+    for args in [(16000, 64, 1024, 1.0, None), (16000, 40, 512, 1.0, None), (8000, 24, 256, 1.0, 3800.0),
+                 (16000, 64, 1024, 1.1, None)]:
+        a = api.mel_matrix(*args)
+        b = O.mel_matrix(*args)
+        assert a.shape == b.shape and np.array_equal(a, b)
+    M = api.mel_matrix(16000, 64, 1024)
+    assert M.min() == 0.0 and M.max() == 1.0 and np.all(M.sum(0) > 0)

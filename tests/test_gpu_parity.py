@@ -171,6 +171,47 @@ def test_stream_groups_do_not_change_results(api, bases, wavs, rng_inputs):
         assert res[1][1][k] == res[3][1][k]
 
 
+def test_mel_separation_mode(api, O, bases, wavs, rng_inputs):
+    """p.B_sep_mode = 'Mel' (SURVEY.md 8f rank 1): separation and adaptation on the 64-band Mel dictionaries
+    (B_Mel_sub of the shipped basis files), gain / block sparsity / resynthesis in the DFT domain
+    (bnmf_sep_event_RT_IS16.m:107-119,165-211,295-319; init_buff.m:60-62)."""
+    h_init, Ad = rng_inputs
+    over = dict(B_sep_mode="Mel", MelConv=1)
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    pcms = [wavs["M03_in"][6000:6000 + 160 * 130], wavs["M04_in"][12000:12000 + 160 * 60 + 9]]
+    ads = np.stack([Ad, np.random.RandomState(4).rand(50, 100)])
+    ctx = api.get_context(0)
+    b = api.Batch(ctx, p, bases["B_DFT_x"], bases["B_DFT_d"], [len(x) for x in pcms], h_init, ads,
+                  B_Mel_x=bases["B_Mel_x"], B_Mel_d=bases["B_Mel_d"])
+    b.enable_trace(True)
+    b.upload(pcms)
+    b.run()
+    outs = b.download()
+    for i, pcm in enumerate(pcms):
+        tr = []
+        ref, g = O.enhance_utterance(pcm, po, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=ads[i],
+                                     B_Mel_x=bases["B_Mel_x"], B_Mel_d=bases["B_Mel_d"], trace=tr)
+        assert len(outs[i]) == len(ref)
+        assert np.array_equal(b.trace(i, "h_iters").astype(int), np.array([t["h_iters"] for t in tr]))
+        assert np.array_equal(b.trace(i, "w_iters").astype(int), np.array([t["w_iters"] for t in tr]))
+        assert sum(t["w_iters"] for t in tr) > 0                       # the Mel-domain adaptation did run
+        worst = max(rel_err(t["Xm_tilde"], x) for t, x in zip(tr, b.trace(i, "Xm_tilde")))
+        assert worst <= SPEC_TOL, worst
+        assert snr_db(ref, outs[i]) >= WAVE_SNR_DB
+        assert np.abs(outs[i].astype(int) - ref.astype(int)).max() <= 1
+        Bm = b.noise_basis(i)
+        assert Bm.shape == (64, 100)
+        assert rel_err(g.B_Mel_d, Bm) <= SPEC_TOL
+    b.close()
+    # Mel mode without the Mel dictionaries, or with MelConv = 0, is refused
+    with pytest.raises(ValueError):
+        api.Batch(ctx, p, bases["B_DFT_x"], bases["B_DFT_d"], [1000], h_init, Ad)
+    with pytest.raises(api.SnmfnatError):
+        api.Batch(ctx, dict(p, MelConv=0), bases["B_DFT_x"], bases["B_DFT_d"], [1000], h_init, Ad,
+                  B_Mel_x=bases["B_Mel_x"], B_Mel_d=bases["B_Mel_d"])
+
+
 def test_unsupported_configs_fail_loudly(api, bases, rng_inputs):
     h_init, Ad = rng_inputs
     for over in (dict(Splice=1), dict(blk_len_sep=2, blk_hop_sep=2)):
