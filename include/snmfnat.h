@@ -204,6 +204,10 @@ int snmfnat_batch_set_mel(snmfnat_batch* b, const double* B_Mel_x, const double*
 /* M = mel_matrix(fs, NbCh, Nfft, warp, fhigh), src/mel_matrix.m:9-38: (Nfft/2+1) x NbCh, column-major.
  * warp <= 0 selects 1, fhigh <= 0 selects fs/2 (the defaults of the reference). */
 int snmfnat_mel_matrix(int fs, int NbCh, int Nfft, double warp, double fhigh, double* M);
+/* Training features of run_basis_train.m:63,70-78 / run_basis_DNMF.m:15,24,33 / run_basis_DNMF_Mel.m:16-27:
+ * out = S_mag.^pow + floor (F x T), or melmat' * that (n1 x T) when melmat (F x n1, column-major) is given. */
+int snmfnat_tf_features(snmfnat_ctx* ctx, const double* S_mag, int F, int64_t T, double pow_, double floor_,
+                        const double* melmat, int n1, double* out);
 /* Scheduling knob, no effect on results: the slots are split into n_groups interleaved groups whose per-hop kernels
  * run on separate CUDA streams, so that the tail of one group's kernel overlaps the next kernel of another group.
  * Default 3 (or the SNMFNAT_GROUPS environment variable). */

@@ -244,6 +244,35 @@ def dnmf_adapt(Y, D, B, *, R_x, R_d, rand, **kw):
     return B_a
 
 
+def run_basis_dnmf(x, d, B, p, *, rand, mel=False):
+    """B_hat = run_basis_DNMF(x,d,B,p), run_basis_DNMF.m:3-55; with ``mel`` the Mel variant
+    run_basis_DNMF_Mel.m:3-93 (features projected with mel_matrix(...)' before the three solves)."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    d = np.asarray(d, dtype=np.float64).ravel()
+    n = min(x.size, d.size)                                           # :5-9
+    x, d = x[:n], d[:n]
+    y = x + d
+    melmat = mel_matrix(p['fs'], p['F_order'], p['fftlength'], 1, p['fs'] / 2).T if mel else None
+
+    def feat(sig):
+        S, _ = stft_fft(sig, p['framelength'], p['frameshift'], p['fftlength'], p['DCbin'], p['win_STFT'], p['preemph'])
+        S = S[:, np.any(S != 0, axis=0)]                              # :14,23,32
+        S = S ** p['pow'] + p['nonzerofloor']                         # :16,25,34 (Splice = 0: frame_splice is identity)
+        return melmat @ S if mel else S
+    X, D, Y = feat(x), feat(d), feat(y)
+    R_x, R_d = p['R_x'], p['R_d']
+    r = R_x + R_d
+    kw = dict(max_iter=p['max_iter'], sparsity=p['sparsity'], conv_eps=p['conv_eps'], cf=p['cf'],
+              cost_check=bool(p['cost_check']))
+    _, A_hat, _ = sparse_nmf(Y, init_w=B, w_update_ind=np.zeros(r, bool), h_update_ind=np.ones(r, bool),
+                             rand=rand, **kw)                         # :37-40
+    B_x, _, _ = sparse_nmf(X, init_w=B[:, :R_x], init_h=A_hat[:R_x, :], w_update_ind=np.ones(R_x, bool),
+                           h_update_ind=np.zeros(R_x, bool), **kw)    # :43-47
+    B_d, _, _ = sparse_nmf(D, init_w=B[:, R_x:r], init_h=A_hat[R_x:r, :], w_update_ind=np.ones(R_d, bool),
+                           h_update_ind=np.zeros(R_d, bool), **kw)    # :49-53
+    return np.concatenate([B_x, B_d], axis=1)
+
+
 # ----------------------------------------------------------------------------
 # STFT / ISTFT
 # ----------------------------------------------------------------------------

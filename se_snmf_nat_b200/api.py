@@ -464,6 +464,65 @@ def DNMF_adapt(Y, D, B, p: dict, *, rand, device: int = 0):
     return out
 
 
+def tf_features(S_mag, pow_: float, floor_: float, melmat=None, *, device: int = 0):
+    """S_mag.^pow + floor, optionally projected on a filterbank (melmat' * X) -- the feature step of
+    run_basis_train.m:63,70-78 / run_basis_DNMF(_Mel).m."""
+    ctx = get_context(device)
+    S = _f64(S_mag)
+    F, T = S.shape
+    mm = _f64(melmat) if melmat is not None else None
+    n1 = mm.shape[1] if mm is not None else 0
+    if mm is not None and mm.shape[0] != F:
+        raise ValueError("melmat must be F x n1")
+    out = np.zeros((n1 if mm is not None else F, T), order="F")
+    check(ctx._lib.snmfnat_tf_features(ctx._h, _dptr(S), F, T, float(pow_), float(floor_), _dptr(mm), n1, _dptr(out)))
+    return out
+
+
+def _dnmf_features(sig, p, melmat, device):
+    S, _ = stft_fft(sig, p["framelength"], p["frameshift"], p["fftlength"], p["DCbin"], p["win_STFT"], p["preemph"],
+                    device=device)
+    S = S[:, np.any(S != 0, axis=0)]                      # X = X(:,any(X,1))
+    if int(p.get("Splice", 0)) != 0:
+        raise SnmfnatError(-4, "frame_splice with Splice > 0 is not implemented")
+    return tf_features(S, p["pow"], p["nonzerofloor"], melmat, device=device)
+
+
+def run_basis_DNMF(x, d, B, p: dict, *, rand=None, mel: bool = False, device: int = 0):
+    """B_hat = run_basis_DNMF(x, d, B, p)         run_basis_DNMF.m:1-57  (mel=False)
+       B_hat = run_basis_DNMF_Mel(x, d, B, p)     run_basis_DNMF_Mel.m:1-95 (mel=True)
+    Discriminative retraining of [B_x B_d] on a clean / noise pair: activations of the mixture with the dictionary
+    fixed (Eq. 6), then W-only updates of the speech atoms on the clean spectrogram and of the noise atoms on the
+    noise spectrogram with those activations (Eq. 7).  Every numeric step runs on the GPU (STFT, features, the three
+    sparse_nmf solves).  `rand(m, n)` supplies rand(r, T) of sparse_nmf.m:134 for the first solve."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    d = np.asarray(d, dtype=np.float64).ravel()
+    n = min(x.size, d.size)
+    x, d = x[:n], d[:n]
+    y = x + d
+    melmat = mel_matrix(p["fs"], p["F_order"], p["fftlength"], 1.0, p["fs"] / 2) if mel else None
+    X = _dnmf_features(x, p, melmat, device)
+    D = _dnmf_features(d, p, melmat, device)
+    Y = _dnmf_features(y, p, melmat, device)
+    R_x, R_d = int(p["R_x"]), int(p["R_d"])
+    B = _f64(B)
+    q = dict(p)
+    q.update(w_update_ind=np.zeros(R_x + R_d, bool), h_update_ind=np.ones(R_x + R_d, bool), init_w=B)
+    q.pop("init_h", None)
+    _, A_hat, _ = sparse_nmf(Y, q, rand=rand, device=device)
+    q.update(w_update_ind=np.ones(R_x, bool), h_update_ind=np.zeros(R_x, bool), init_w=B[:, :R_x], init_h=A_hat[:R_x, :],
+             r=R_x)
+    B_hat_x, _, _ = sparse_nmf(X, q, device=device)
+    q.update(w_update_ind=np.ones(R_d, bool), h_update_ind=np.zeros(R_d, bool), init_w=B[:, R_x:R_x + R_d],
+             init_h=A_hat[R_x:R_x + R_d, :], r=R_d)
+    B_hat_d, _, _ = sparse_nmf(D, q, device=device)
+    return np.concatenate([B_hat_x, B_hat_d], axis=1)
+
+
+def run_basis_DNMF_Mel(x, d, B, p: dict, **kw):
+    return run_basis_DNMF(x, d, B, p, mel=True, **kw)
+
+
 def stft_fft(s, sz, shift, fftlen, DCbin, win, preemph, *, device: int = 0):
     """[S_mag, S_phase] = stft_fft(s, sz, shift, fftlen, DCbin, win, preemph)     src/stft_fft.m:1-37."""
     ctx = get_context(device)

@@ -2,6 +2,7 @@
 // projection of the separation input (src/bnmf_sep_event_RT_IS16.m:107-119), the Mel -> DFT conversion of the separated
 // spectra (:165-172,187-195,205-211) and the Mel image of the noise history the adaptation solves on (:295-301).
 // The H-solve and W-solve themselves are the ordinary kernels run on a Mel-sized view of the slot state.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 #include "online.cuh"
@@ -148,7 +149,59 @@ void launch_mel_hist(snmfnat_ctx* ctx, const OnlineDims& d, const SlotState& st,
   check_launch(ctx, "mel_hist_kernel");
 }
 
+// Training features (run_basis_train.m:63,70-78; run_basis_DNMF.m:15,24,33; run_basis_DNMF_Mel.m:16-27): X = S.^pow + floor
+// and, when a filterbank is given, X_Mel = melmat' * X.  One CTA per frame; in/out column-major (bins x frames).
+__global__ void tf_features_kernel(const double* __restrict__ S, int F, long long T, double pw, double flr,
+                                   const double* __restrict__ M /* [n1][F] or null */, int n1, double* __restrict__ out) {
+  extern __shared__ double xs[];
+  for (long long t = blockIdx.x; t < T; t += gridDim.x) {
+    const double* s = S + (size_t)t * F;
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      const double m = s[f];
+      const double x = (pw == 2.0 ? m * m : (pw == 1.0 ? m : pow(m, pw))) + flr;
+      if (M) xs[f] = x; else out[(size_t)t * F + f] = x;
+    }
+    if (!M) continue;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int b = warp; b < n1; b += nw) {
+      const double* m = M + (size_t)b * F;
+      double acc = 0.0;
+      for (int f = lane; f < F; f += 32) acc = fma(m[f], xs[f], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) out[(size_t)t * n1 + b] = acc;
+    }
+  }
+}
+
 }  // namespace snmfnat
+
+extern "C" int snmfnat_tf_features(snmfnat_ctx* ctx, const double* S_mag, int F, int64_t T, double pow_, double floor_,
+                                   const double* melmat, int n1, double* out) {
+  using namespace snmfnat;
+  SN_API_BEGIN
+  SN_REQUIRE(ctx && S_mag && out && F > 0 && T >= 0, SNMFNAT_EINVAL, "bad argument");
+  SN_REQUIRE(melmat == nullptr || n1 > 0, SNMFNAT_EINVAL, "n1 must be positive with a filterbank");
+  SN_CUDA(cudaSetDevice(ctx->device));
+  if (T == 0) return SNMFNAT_OK;
+  DevBuf<double> dS, dM, dO;
+  dS.alloc((size_t)F * T);
+  dO.alloc((size_t)(melmat ? n1 : F) * T);
+  SN_CUDA(cudaMemcpyAsync(dS.p, S_mag, dS.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (melmat) {  // host n2 x n1 column-major == device [n1][F]
+    dM.alloc((size_t)n1 * F);
+    SN_CUDA(cudaMemcpyAsync(dM.p, melmat, dM.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(T, (int64_t)ctx->sm_count * 8);
+  tf_features_kernel<<<grid, 256, (size_t)F * sizeof(double), ctx->stream>>>(dS.p, F, T, pow_, floor_, melmat ? dM.p : nullptr,
+                                                                             n1, dO.p);
+  count_launch(ctx);
+  check_launch(ctx, "tf_features_kernel");
+  SN_CUDA(cudaMemcpyAsync(out, dO.p, dO.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SN_CUDA(cudaStreamSynchronize(ctx->stream));
+  SN_API_END
+}
 
 extern "C" int snmfnat_mel_matrix(int fs, int NbCh, int Nfft, double warp, double fhigh, double* M) {
   SN_API_BEGIN

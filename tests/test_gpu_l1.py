@@ -210,3 +210,35 @@ def test_per_hop_stream_matches_oracle_and_batch(api, O, bases, wavs, rng_inputs
             ref.append(O.to_int16(ola[:160]))
     assert np.abs(np.concatenate(ref).astype(int) - out.astype(int)).max() <= 1
     g.close()
+
+
+@pytest.mark.parametrize("mel", [False, True], ids=["run_basis_DNMF", "run_basis_DNMF_Mel"])
+def test_dnmf_basis_retraining_matches_oracle(api, O, wavs, mel):
+    """run_basis_DNMF.m / run_basis_DNMF_Mel.m: STFT of clean, noise and mixture, activations of
+    the mixture with the dictionary fixed, then W-only updates of the two halves -- every step on the GPU."""
+    rs = np.random.RandomState(9)
+    x = wavs["M03_in"][8000:8000 + 16000].astype(np.float64)
+    d = wavs["M04_in"][3000:3000 + 15000].astype(np.float64) * 0.5        # shorter: both are cut to its length (:5-9)
+    R_x, R_d = 10, 6
+    over = dict(R_x=R_x, R_d=R_d, max_iter=12, conv_eps=1e-4)
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    F = 64 if mel else 513
+    B = rs.rand(F, R_x + R_d) + 0.05
+    h0 = rs.rand(R_x + R_d, 200)
+    rand = lambda m, n: h0[:m, :n].copy()
+    B_hat = api.run_basis_DNMF(x, d, B, p, rand=rand, mel=mel)
+    B_ref = O.run_basis_dnmf(x, d, B, po, rand=rand, mel=mel)
+    assert B_hat.shape == B_ref.shape == (F, R_x + R_d)
+    assert rel_err(B_ref, B_hat) < TOL, rel_err(B_ref, B_hat)
+    assert np.allclose(np.linalg.norm(B_hat, axis=0), 1.0, atol=1e-9)     # sparse_nmf.m:242
+    assert rel_err(B, B_hat) > 1e-2                                        # it did move
+
+
+def test_tf_features(api, O):
+    rs = np.random.RandomState(2)
+    S = rs.rand(513, 37)
+    M = O.mel_matrix(16000, 64, 1024, 1, 8000)
+    np.testing.assert_allclose(api.tf_features(S, 2.0, 1e-9), S ** 2 + 1e-9, rtol=1e-15)
+    np.testing.assert_allclose(api.tf_features(S, 1.5, 1e-9), S ** 1.5 + 1e-9, rtol=1e-13)
+    np.testing.assert_allclose(api.tf_features(S, 2.0, 1e-9, M), M.T @ (S ** 2 + 1e-9), rtol=1e-12)
