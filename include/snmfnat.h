@@ -196,7 +196,7 @@ int snmfnat_batch_run(snmfnat_batch* b);
 /* Device -> host copy of the enhanced int16 signals; out[u] must hold snmfnat_batch_out_len(b,u) samples
  * ((floor(len/frameshift)+1)*frameshift, filewise_run_IS16.m:146,162-165). */
 /* B_sep_mode = 'Mel' (bnmf_sep_event_RT_IS16.m:107-119,165-211,295-319): the separation and the noise-basis
- * adaptation run on n1 Mel bands.  B_Mel_x n1 x R_x, B_Mel_d n1 x R_d (the B_Mel_sub of basis/*.mat); melmat is the
+ * adaptation run on n1 Mel bands.  B_Mel_x n1 x R_x, B_Mel_d n1 x R_d (the B_Mel_sub of the shipped basis files); melmat is the
  * n2 x n1 matrix src/mel_matrix.m returns, or NULL to have the library build it the way init_buff.m:60-62 does.
  * Must be called once, before snmfnat_batch_run, when p.B_sep_mode == SNMFNAT_SEP_MEL (MelConv = 1 only);
  * snmfnat_batch_get_noise_basis then returns the adapted B_Mel_d (n1 x R_d). */

@@ -1,8 +1,9 @@
-// MEX gateway: snmfnat_enhance_files(paths_in, paths_out, B_DFT_x, B_DFT_d, p [, chain_id])
+// MEX gateway: snmfnat_enhance_files(paths_in, paths_out, B_DFT_x, B_DFT_d, p [, chain_id [, B_Mel_x, B_Mel_d]])
 // The hop loops of filewise_run_IS16.m:54-186 / src/NTF_sep_event_RT.m:12-156 for a whole list of files in ONE device
 // call (no per-hop PCIe crossing): reads the int16 samples after the 44-byte WAV header (:92-97), enhances them with
 // snmfnat_enhance_batch, writes 16-bit mono WAV files.  chain_id (optional, one per file) reproduces the B_D_u.mat
 // carry-over of run_ntf_sep_RT: files with equal id are processed in list order on one adapted noise dictionary.
+// With p.B_sep_mode = 'Mel' the Mel dictionaries (B_Mel_sub of the basis files) are the 7th and 8th argument.
 #include <cstdio>
 #include "snmfnat_mex.h"
 using namespace snmex;
@@ -32,7 +33,8 @@ static void write_wav(const std::string& path, const std::vector<int16_t>& x, in
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   (void)plhs;
-  if (nrhs < 5 || nlhs > 0) mexErrMsgIdAndTxt("snmfnat:usage", "snmfnat_enhance_files(paths_in,paths_out,B_DFT_x,B_DFT_d,p[,chain_id])");
+  if (nrhs < 5 || nlhs > 0)
+    mexErrMsgIdAndTxt("snmfnat:usage", "snmfnat_enhance_files(paths_in,paths_out,B_DFT_x,B_DFT_d,p[,chain_id[,B_Mel_x,B_Mel_d]])");
   if (!mxIsCell(prhs[0]) || !mxIsCell(prhs[1])) mexErrMsgIdAndTxt("snmfnat:usage", "paths must be cell arrays of strings");
   const size_t n = mxGetNumberOfElements(prhs[0]);
   const mxArray* p = prhs[4];
@@ -67,10 +69,24 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   }
   const mxArray *ws = field(p, "win_STFT"), *wi = field(p, "win_ISTFT");
   if (!ws || !wi) mexErrMsgIdAndTxt("snmfnat:param", "p.win_STFT / p.win_ISTFT missing");
-  check(snmfnat_enhance_batch(ctx(), &q, mxGetPr(ws), mxGetPr(wi), mat(prhs[2], F, q.R_x, "B_DFT_x"),
-                              mat(prhs[3], F, q.R_d, "B_DFT_d"), (int)F, (int)n, pin.data(), len.data(),
-                              chain.empty() ? nullptr : chain.data(), mxGetPr(h0), ad.data(),
-                              (int64_t)q.R_a * q.m_a, pout.data()));
+  snmfnat_batch* bt = nullptr;
+  check(snmfnat_batch_create(ctx(), &q, mxGetPr(ws), mxGetPr(wi), mat(prhs[2], F, q.R_x, "B_DFT_x"),
+                             mat(prhs[3], F, q.R_d, "B_DFT_d"), (int)F, (int)n, len.data(),
+                             chain.empty() ? nullptr : chain.data(), mxGetPr(h0), ad.data(), (int64_t)q.R_a * q.m_a, &bt));
+  int rc = 0;
+  if (q.B_sep_mode == SNMFNAT_SEP_MEL) {   // filewise_run_IS16.m:46-51: B1_x / B1_d are the Mel dictionaries
+    if (nrhs < 8) {
+      snmfnat_batch_destroy(bt);
+      mexErrMsgIdAndTxt("snmfnat:usage", "p.B_sep_mode = 'Mel' needs B_Mel_x and B_Mel_d (arguments 7 and 8)");
+    }
+    const size_t n1 = mxGetM(prhs[6]);
+    rc = snmfnat_batch_set_mel(bt, mat(prhs[6], n1, q.R_x, "B_Mel_x"), mat(prhs[7], n1, q.R_d, "B_Mel_d"), (int)n1, nullptr);
+  }
+  if (!rc) rc = snmfnat_batch_upload(bt, pin.data());
+  if (!rc) rc = snmfnat_batch_run(bt);
+  if (!rc) rc = snmfnat_batch_download(bt, pout.data());
+  snmfnat_batch_destroy(bt);
+  check(rc);
   mxDestroyArray(h0);
   for (size_t i = 0; i < n; ++i) write_wav(po[i], out[i], q.fs);
 }
