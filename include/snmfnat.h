@@ -208,6 +208,13 @@ int snmfnat_mel_matrix(int fs, int NbCh, int Nfft, double warp, double fhigh, do
  * out = S_mag.^pow + floor (F x T), or melmat' * that (n1 x T) when melmat (F x n1, column-major) is given. */
 int snmfnat_tf_features(snmfnat_ctx* ctx, const double* S_mag, int F, int64_t T, double pow_, double floor_,
                         const double* melmat, int n1, double* out);
+/* [C, A] = GIST_NTF(p, B, S_mag)  (src/GIST_NTF.m:1-160; cost_check = -1) and GIST_NTF_C (src/GIST_NTF_C.m; cost_check =
+ * p.cost_check): KL tensor factorisation S(h,n,m) ~ sum_k C(h,k) B(n,k) A(m,k) with only the channel gains updated.
+ * S_mag Channel x N x M and B N x K column-major; C_init = rand(Channel, K) drawn by the host (:14); A M x K or NULL for
+ * the reference's ones(M, K) (:16).  C_out Channel x K; div / cost hold max_iter doubles (may be NULL). */
+int snmfnat_gist_ntf(snmfnat_ctx* ctx, const double* S_mag, int Channel, int N, int M, const double* B, int K,
+                     const double* C_init, const double* A, double sparsity, double flr, int max_iter, double conv_eps,
+                     int cost_check, double* C_out, double* div, double* cost, int* iters);
 /* Scheduling knob, no effect on results: the slots are split into n_groups interleaved groups whose per-hop kernels
  * run on separate CUDA streams, so that the tail of one group's kernel overlaps the next kernel of another group.
  * Default 3 (or the SNMFNAT_GROUPS environment variable). */

@@ -244,6 +244,42 @@ def dnmf_adapt(Y, D, B, *, R_x, R_d, rand, **kw):
     return B_a
 
 
+def gist_ntf(p, B, S_mag, *, rand, A=None, variant_c=False):
+    """[C,A] = GIST_NTF(p,B,S_mag), src/GIST_NTF.m:8-155 (``variant_c``: src/GIST_NTF_C.m, objective gated by
+    p.cost_check).  S_mag Channel x N x M.  Only C is updated (C_UPDATE=1, A_UPDATE=0, :4-6)."""
+    S = np.asarray(S_mag, dtype=np.float64)
+    Ch, N, M = S.shape
+    B = np.array(B, dtype=np.float64)
+    K = B.shape[1]
+    C = np.array(rand(Ch, K), dtype=np.float64)                       # :14
+    A = np.ones((M, K)) if A is None else np.asarray(A, dtype=np.float64)   # :16
+    flr = p['nonzerofloor']
+    Bn = np.sqrt(np.sum(B ** 2, axis=0))                              # :27-29
+    B = B / Bn
+    C = C * Bn
+    xhat = lambda: np.maximum(np.einsum('hk,nk,mk->hnm', C, B, A), flr)   # kr(A,B,C) summed over k, :40-42
+    X = xhat()
+    P = np.maximum(S / X, flr)
+    div_l, cost_l, its, last = [], [], 0, None
+    for i in range(1, p['max_iter'] + 1):
+        PBA = np.maximum(np.einsum('hnm,nk,mk->hk', P, B, A), flr)    # :96-113
+        OBA = np.maximum(np.einsum('nk,mk->k', B, A), flr)[None, :]
+        C = np.maximum(C * PBA / (OBA + p['sparsity']), flr)          # :114-115
+        X = xhat()
+        P = np.maximum(S / X, flr)
+        its = i
+        if (not variant_c) or p['cost_check']:
+            with np.errstate(divide='ignore', invalid='ignore'):
+                div = float(np.sum(S * np.log(S / X) - S + X))        # :131
+            cost = div + float(np.sum(p['sparsity'] * C))
+            div_l.append(div)
+            cost_l.append(cost)
+            if i > 1 and p['conv_eps'] > 0 and abs(cost - last) / last < p['conv_eps']:
+                break
+            last = cost
+    return C, A, dict(div=np.array(div_l), cost=np.array(cost_l), iters=its)
+
+
 def run_basis_dnmf(x, d, B, p, *, rand, mel=False):
     """B_hat = run_basis_DNMF(x,d,B,p), run_basis_DNMF.m:3-55; with ``mel`` the Mel variant
     run_basis_DNMF_Mel.m:3-93 (features projected with mel_matrix(...)' before the three solves)."""

@@ -123,6 +123,8 @@ SIGNATURES = {
     "snmfnat_batch_set_groups": (C.c_int, [_vp, C.c_int]),
     "snmfnat_batch_set_mel": (C.c_int, [_vp, _dp, _dp, C.c_int, _dp]),
     "snmfnat_tf_features": (C.c_int, [_vp, _dp, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, C.c_int, _dp]),
+    "snmfnat_gist_ntf": (C.c_int, [_vp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_int,
+                                  C.c_double, C.c_int, _dp, _dp, _dp, _P(C.c_int)]),
     "snmfnat_mel_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "snmfnat_batch_get_profile": (C.c_int, [_vp, _dp, _P(C.c_int64)]),
     "snmfnat_batch_get_noise_basis": (C.c_int, [_vp, C.c_int, _dp]),

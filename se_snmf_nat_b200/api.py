@@ -464,6 +464,32 @@ def DNMF_adapt(Y, D, B, p: dict, *, rand, device: int = 0):
     return out
 
 
+def GIST_NTF(p: dict, B, S_mag, *, rand, A=None, variant_c: bool = False, device: int = 0):
+    """[C, A] = GIST_NTF(p, B, S_mag)      src/GIST_NTF.m:1-160  (variant_c: src/GIST_NTF_C.m, objective only when
+    p.cost_check).  S_mag is Channel x N x M, B N x K; `rand(Channel, K)` supplies the rand of :14.  Returns
+    (C, A, objective) with A = ones(M, K) unless given."""
+    ctx = get_context(device)
+    S = np.asfortranarray(np.asarray(S_mag, dtype=np.float64))
+    Ch, N, M = S.shape
+    B = _f64(B)
+    K = B.shape[1]
+    if B.shape[0] != N:
+        raise ValueError("B must be N x K with N = size(S_mag, 2)")
+    C0 = _f64(np.asarray(rand(Ch, K), dtype=np.float64))
+    Aa = _f64(A) if A is not None else None
+    max_iter = int(p.get("max_iter", 100))
+    Cout = np.zeros((Ch, K), order="F")
+    div = np.zeros(max(max_iter, 1))
+    cost = np.zeros(max(max_iter, 1))
+    its = C.c_int(0)
+    cc = int(bool(p.get("cost_check", 1))) if variant_c else -1
+    check(ctx._lib.snmfnat_gist_ntf(ctx._h, _dptr(S), Ch, N, M, _dptr(B), K, _dptr(C0), _dptr(Aa), float(p.get("sparsity", 0.0)),
+                                    float(p.get("nonzerofloor", 1e-9)), max_iter, float(p.get("conv_eps", 0.0)), cc,
+                                    _dptr(Cout), _dptr(div), _dptr(cost), C.byref(its)))
+    k = its.value if cc != 0 else 0
+    return Cout, (Aa if Aa is not None else np.ones((M, K))), {"div": div[:k], "cost": cost[:k], "iters": its.value}
+
+
 def tf_features(S_mag, pow_: float, floor_: float, melmat=None, *, device: int = 0):
     """S_mag.^pow + floor, optionally projected on a filterbank (melmat' * X) -- the feature step of
     run_basis_train.m:63,70-78 / run_basis_DNMF(_Mel).m."""

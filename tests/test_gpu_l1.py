@@ -242,3 +242,30 @@ def test_tf_features(api, O):
     np.testing.assert_allclose(api.tf_features(S, 2.0, 1e-9), S ** 2 + 1e-9, rtol=1e-15)
     np.testing.assert_allclose(api.tf_features(S, 1.5, 1e-9), S ** 1.5 + 1e-9, rtol=1e-13)
     np.testing.assert_allclose(api.tf_features(S, 2.0, 1e-9, M), M.T @ (S ** 2 + 1e-9), rtol=1e-12)
+
+
+@pytest.mark.parametrize("variant_c,with_a", [(False, False), (True, False), (False, True)])
+def test_gist_ntf_matches_oracle(api, O, variant_c, with_a):
+    """GIST_NTF / GIST_NTF_C (6-channel KL tensor factorisation with fixed dictionary, channel gains updated)."""
+    rs = np.random.RandomState(13)
+    Ch, N, M, K = 6, 129, 23, 17
+    B = rs.rand(N, K) + 0.01
+    Ct = rs.rand(Ch, K)
+    S = np.einsum('hk,nk,mk->hnm', Ct, B, rs.gamma(1.0, 1.0, (M, K))) + 1e-6
+    C0 = rs.rand(Ch, K)
+    rand = lambda a, b: C0[:a, :b].copy()
+    A = rs.rand(M, K) + 0.1 if with_a else None
+    p = dict(max_iter=25, conv_eps=1e-4, sparsity=0.5, nonzerofloor=1e-9, cost_check=1)
+    Cg, Ag, og = api.GIST_NTF(p, B, S, rand=rand, A=A, variant_c=variant_c)
+    Cr, Ar, orf = O.gist_ntf(p, B, S, rand=rand, A=A, variant_c=variant_c)
+    assert og["iters"] == orf["iters"]
+    assert rel_err(Cr, Cg) < 1e-9
+    np.testing.assert_allclose(og["cost"], orf["cost"], rtol=1e-10)
+    assert np.all(np.diff(og["cost"]) <= 1e-9 * og["cost"][:-1])        # KL + L1 objective does not increase
+    assert Ag.shape == (M, K)
+    # GIST_NTF_C with p.cost_check = 0 runs max_iter iterations and reports no objective
+    if variant_c:
+        Cg2, _, og2 = api.GIST_NTF(dict(p, cost_check=0, max_iter=5), B, S, rand=rand, variant_c=True)
+        Cr2, _, or2 = O.gist_ntf(dict(p, cost_check=0, max_iter=5), B, S, rand=rand, variant_c=True)
+        assert og2["iters"] == or2["iters"] == 5 and og2["cost"].size == 0
+        assert rel_err(Cr2, Cg2) < 1e-9
