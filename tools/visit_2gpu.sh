@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_n2.log 2>&1
+tail -1 gpurun_out/bench_n2.log | cut -c1-600
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload train --steps 10 --warmup 3 > gpurun_out/bench_train_n2_weak.log 2>&1
+tail -1 gpurun_out/bench_train_n2_weak.log | cut -c1-400
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --workload train --train-scaling strong --train-frames 2500000 --steps 10 --warmup 3 > gpurun_out/bench_train_n2_strong.log 2>&1
+tail -1 gpurun_out/bench_train_n2_strong.log | cut -c1-400
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/bench_ref_n2.log 2>&1
+tail -1 gpurun_out/bench_ref_n2.log | cut -c1-400
