@@ -454,27 +454,31 @@ void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScala
 // =====================================================================================================
 // W-solve, fast path
 // =====================================================================================================
-constexpr int WF_WARPS = 17;            // 16 tile warps + 1 warp for the leftover tile
-constexpr int WF_THREADS = WF_WARPS * 32;
-constexpr int WF_CL = 4;
-constexpr int WF_TPC = 16;              // full tiles per CTA
+// Two geometries of the same kernel (template parameters CL = CTAs per cluster, TPC = full 8-row tiles per CTA):
+//   <4,16, V in shared memory>  17 warps per CTA, one CTA per SM (the slice of V = lambda_d_blk is staged once)
+//   <8, 8, V from L2>           9 warps per CTA, 82 KB of shared memory -> TWO CTAs (of different streams) per SM: while
+//                               one sits in a reduction / cluster exchange the other keeps the FP64 pipe busy.  V is
+//                               read once per iteration straight from L2 (one group ahead of its use), which is what
+//                               frees the shared memory.
+constexpr int WF_MAX_WARPS = 17;
 
-template <int KT>
+template <int KT, int CL, int TPC, bool VSMEM>
 struct WfLayout {
   static constexpr int KMAX = KT * 8;
   static constexpr int XN = 3 * KMAX + 8;
+  static constexpr int WARPS = TPC + 1;      // TPC tile warps + 1 warp for the leftover tile
   int NP, HSd, VS, VROWS;
   size_t off_H, off_V, off_red, off_recv, off_hs, off_wn, off_tot, off_tab, off_scratch, off_bar, bytes;
   __host__ __device__ WfLayout(int m_a) {
     NP = (m_a + 15) / 16 * 16;
     HSd = NP + ((2 - NP % 8) + 8) % 8;          // == 2 (mod 8): conflict-free fragment loads in both GEMMs
-    VROWS = (WF_TPC + 1) * 8;                   // 136 local rows (leftover tile included)
+    VROWS = (TPC + 1) * 8;                      // local rows (leftover tile included)
     VS = VROWS + 1;                             // odd stride: conflict-free (t, row) fragment reads
     size_t o = 0;
     off_H = o;       o += (size_t)KMAX * HSd;
-    off_V = o;       o += (size_t)NP * VS;
-    off_red = o;     o += (size_t)2 * WF_WARPS * KMAX;
-    off_recv = o;    o += (size_t)2 * WF_CL * XN;   // [2][4][XN] partials pushed by the 4 CTAs
+    off_V = o;       o += VSMEM ? (size_t)NP * VS : 0;
+    off_red = o;     o += (size_t)2 * WARPS * KMAX;
+    off_recv = o;    o += (size_t)2 * CL * XN;      // [2][CL][XN] partials pushed by the CTAs of the cluster
     off_hs = o;      o += KMAX;
     off_wn = o;      o += KMAX;
     off_tot = o;     o += 2 * KMAX;
@@ -498,16 +502,18 @@ __device__ __forceinline__ double rows8_sum_f(double v) {
   return v;
 }
 
-template <int KT>
-__global__ void __cluster_dims__(WF_CL, 1, 1) __launch_bounds__(WF_THREADS, 1)
+template <int KT, int CL, int TPC, bool VSMEM>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__((TPC + 1) * 32, VSMEM ? 1 : 2)
 wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr, int has_trace, int g_step,
                    const double2* __restrict__ log_tab) {
-  using LT = WfLayout<KT>;
+  using LT = WfLayout<KT, CL, TPC, VSMEM>;
   constexpr int KMAX = LT::KMAX;
   constexpr int XN = LT::XN;
+  constexpr int WARPS = LT::WARPS;
+  constexpr int THREADS = WARPS * 32;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int slot = d.slot0 + (int)(blockIdx.x / WF_CL) * d.slot_stride;
+  const int slot = d.slot0 + (int)(blockIdx.x / CL) * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;
   if (!st.do_update[slot]) return;  // uniform over the cluster
@@ -519,11 +525,11 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   const LT L(n);
   const int HSd = L.HSd, NP = L.NP, VS = L.VS;
 
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(1024) double smem[];
   double* Hs = smem + L.off_H;
-  double* Vs = smem + L.off_V;        // [NP][VS]: V slice of this CTA, pad = floor
-  double* red = smem + L.off_red;     // [2][WF_WARPS][KMAX]
-  double* recv = smem + L.off_recv;   // [2][4][XN]
+  double* Vs = smem + L.off_V;        // [NP][VS]: V slice of this CTA, pad = floor (VSMEM only)
+  double* red = smem + L.off_red;     // [2][WARPS][KMAX]
+  double* recv = smem + L.off_recv;   // [2][CL][XN]
   const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem + L.off_bar);
   if (tid == 0) {
     hf_mbar_init(bar0, 1);
@@ -546,35 +552,37 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   const double* __restrict__ Vg = st.lam_blk + (size_t)slot * n * LDF;
   const double* __restrict__ Adb = st.Ad_blk + (size_t)slot * n * R_a;
 
-  // tiles: rank r owns full tiles [16r, 16r+16); the leftover rows (F % 8) form one more tile on the last rank
+  // tiles: rank r owns full tiles [TPC r, TPC r + TPC); the leftover rows (F % 8) form one more tile on the last rank
   const int NFT = F / 8;
   const int nleft = F - NFT * 8;
-  const int row0 = rank * WF_TPC * 8;                 // first global row of this CTA's slice
-  int tile_local = warp;                               // local tile index 0..16
+  const int row0 = rank * TPC * 8;                     // first global row of this CTA's slice
+  int tile_local = warp;                               // local tile index 0..TPC
   bool tile_valid;
-  if (warp < WF_TPC) tile_valid = (rank * WF_TPC + warp) < NFT;
-  else tile_valid = (nleft > 0) && (rank == WF_CL - 1);
+  if (warp < TPC) tile_valid = (rank * TPC + warp) < NFT;
+  else tile_valid = (nleft > 0) && (rank == CL - 1);
   int frow = row0 + tile_local * 8 + g;                // global row of this lane's fragment row
-  if (warp == WF_TPC) frow = NFT * 8 + g;
+  if (warp == TPC) frow = NFT * 8 + g;
   const bool row_valid = tile_valid && frow < F;
-  // local row index inside Vs: tiles 0..15 -> rows 0..127, leftover tile -> rows 128..135
+  // local row index inside Vs: tiles 0..TPC-1 -> rows 0..8 TPC-1, leftover tile -> the 8 rows after them
   const int vrow = tile_local * 8 + g;
 
   // ---- stage the log table, V slice (v = max(v, flr), pad = flr), W fragments ----
   if (tid < 128) tab[tid] = log_tab[tid];
-  for (int t = warp; t < NP; t += WF_WARPS)
-    for (int r = lane; r < L.VROWS; r += 32) {
-      int fr_ = row0 + r;
-      bool ok;
-      if (r < WF_TPC * 8) ok = fr_ < NFT * 8;
-      else {
-        fr_ = NFT * 8 + (r - WF_TPC * 8);
-        ok = (rank == WF_CL - 1) && fr_ < F;
+  if (VSMEM) {
+    for (int t = warp; t < NP; t += WARPS)
+      for (int r = lane; r < L.VROWS; r += 32) {
+        int fr_ = row0 + r;
+        bool ok;
+        if (r < TPC * 8) ok = fr_ < NFT * 8;
+        else {
+          fr_ = NFT * 8 + (r - TPC * 8);
+          ok = (rank == CL - 1) && fr_ < F;
+        }
+        double x = flr;
+        if (ok && t < n) x = fmax(Vg[(size_t)t * LDF + fr_], flr);                // sparse_nmf.m:169
+        Vs[(size_t)t * VS + r] = x;
       }
-      double x = flr;
-      if (ok && t < n) x = fmax(Vg[(size_t)t * LDF + fr_], flr);                // sparse_nmf.m:169
-      Vs[(size_t)t * VS + r] = x;
-    }
+  }
   double w[KT][2], gacc[KT][2];
 #pragma unroll
   for (int j = 0; j < KT; ++j)
@@ -589,7 +597,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 
   // per-warp partial of a per-column quantity -> red[which][warp][k]
   auto warp_partial = [&](int which, auto&& f) {
-    double* rw = red + ((size_t)which * WF_WARPS + warp) * KMAX;
+    double* rw = red + ((size_t)which * WARPS + warp) * KMAX;
 #pragma unroll
     for (int j = 0; j < KT; ++j)
 #pragma unroll
@@ -598,46 +606,46 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         if (g == 0) rw[8 * j + 2 * tg + e] = s;
       }
   };
-  // CTA partial (fixed warp order) PUSHED to the 4 CTAs of the cluster (st.async, bytes counted on the receiver's
+  // CTA partial (fixed warp order) PUSHED to the CTAs of the cluster (st.async, bytes counted on the receiver's
   // mbarrier: no cluster barrier / fence); totals in rank order -> tot[which][k]
   unsigned rnd = 0;
   auto cluster_combine = [&](int nwhich, bool with_cost, double* extra_out, bool inv_sqrt = false) {
     __syncthreads();
     const unsigned buf = rnd & 1u, parity = (rnd >> 1) & 1u;
     const unsigned bar = bar0 + 8u * buf;
-    double* rb = recv + (size_t)buf * WF_CL * XN;
+    double* rb = recv + (size_t)buf * CL * XN;
     const int npay = nwhich * KMAX;
     const unsigned my_row = (unsigned)__cvta_generic_to_shared(rb + (size_t)rank * XN);
-    if (tid == 0) hf_mbar_expect_tx(bar, (unsigned)(WF_CL * (npay + 1) * sizeof(double)));
+    if (tid == 0) hf_mbar_expect_tx(bar, (unsigned)(CL * (npay + 1) * sizeof(double)));
     if (tid < npay) {
       const int which = tid / KMAX, k = tid - which * KMAX;
       double s = 0.0;
 #pragma unroll
-      for (int ww = 0; ww < WF_WARPS; ++ww) s += red[((size_t)which * WF_WARPS + ww) * KMAX + k];
+      for (int ww = 0; ww < WARPS; ++ww) s += red[((size_t)which * WARPS + ww) * KMAX + k];
       const unsigned la = my_row + 8u * (unsigned)tid;
 #pragma unroll
-      for (int c = 0; c < WF_CL; ++c) hf_st_async(hf_mapa(la, c), s, hf_mapa(bar, c));
-    } else if (tid == WF_THREADS - 1) {  // per-warp cost partials, fixed order
+      for (int c = 0; c < CL; ++c) hf_st_async(hf_mapa(la, c), s, hf_mapa(bar, c));
+    } else if (tid == THREADS - 1) {  // per-warp cost partials, fixed order
       double s = 0.0;
       if (with_cost) {
 #pragma unroll
-        for (int ww = 0; ww < WF_WARPS; ++ww) s += scratch[ww];
+        for (int ww = 0; ww < WARPS; ++ww) s += scratch[ww];
       }
       const unsigned la = my_row + 8u * (unsigned)(3 * KMAX);
 #pragma unroll
-      for (int c = 0; c < WF_CL; ++c) hf_st_async(hf_mapa(la, c), s, hf_mapa(bar, c));
+      for (int c = 0; c < CL; ++c) hf_st_async(hf_mapa(la, c), s, hf_mapa(bar, c));
     }
     hf_mbar_wait(bar, parity);
     if (tid < npay) {
       double s = 0.0;
 #pragma unroll
-      for (int c = 0; c < WF_CL; ++c) s += rb[(size_t)c * XN + tid];
+      for (int c = 0; c < CL; ++c) s += rb[(size_t)c * XN + tid];
       tot[tid] = inv_sqrt ? 1.0 / sqrt(s) : s;   // one sqrt + division per column instead of one per element
     }
     if (extra_out) {
       double s = 0.0;
 #pragma unroll
-      for (int c = 0; c < WF_CL; ++c) s += rb[(size_t)c * XN + 3 * KMAX];
+      for (int c = 0; c < CL; ++c) s += rb[(size_t)c * XN + 3 * KMAX];
       *extra_out = s;
     }
     ++rnd;
@@ -655,7 +663,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 #pragma unroll
     for (int e = 0; e < 2; ++e) w[j][e] = w[j][e] / wn_s[8 * j + 2 * tg + e];   // :159
   // H = init_h .* wn (:160), zero padded; row sums (constant over the solve)
-  for (int k = warp; k < KMAX; k += WF_WARPS) {
+  for (int k = warp; k < KMAX; k += WARPS) {
     const bool kv = k < Ru;
     const int src = kv ? idx_up[k] : 0;
     const double wn = wn_s[k];
@@ -680,11 +688,24 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   double last_cost = INFINITY, cost = 0.0;
   const int ngroups = NP / 16;
   const double* vbase = Vs + vrow;
+  // V straight from L2 (!VSMEM): this lane's 4 history columns of group tgp, floored; padding = floor
+  const double* vglob = Vg + (row_valid ? frow : 0);
+  auto load_v4 = [&](int tgp, double (&dst)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = tgp * 16 + 4 * tg + q;
+      double x = flr;
+      if (row_valid && t < n) x = fmax(__ldg(vglob + (size_t)t * LDF), flr);        // sparse_nmf.m:169
+      dst[q] = x;
+    }
+  };
   for (;;) {
     double cacc = 0.0;
     const bool want_cost = sc.cost_check && it >= 1;
     for (int tgp = 0; tgp < (tile_valid ? ngroups : 0); ++tgp) {   // a warp without a tile only takes part in the reductions
       const int n0 = tgp * 16;
+      double vcur[4];
+      if (!VSMEM) load_v4(tgp, vcur);                                // in flight during GEMM 1 (and the other CTA's work)
       // GEMM 1: lambda tile = W * H for 16 history columns (even columns -> c0, odd -> c1)
       double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
 #pragma unroll
@@ -702,7 +723,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const double lam = fmax((q & 1) ? c1[q >> 1] : c0[q >> 1], flr);                 // :243
-        const double v = vbase[(size_t)(n0 + 4 * tg + q) * VS];
+        const double v = VSMEM ? vbase[(size_t)(n0 + 4 * tg + q) * VS] : vcur[q];
         const double r = v * fast_rcp(lam);
         if (want_cost) cacc += fma(v, fast_log(r, tab), lam - v);                         // :250
         rt[q] = r;
@@ -789,10 +810,10 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   {
     // the not-updated adaptable atoms move to the front; columns >= R_a never change and are valid in both
     // buffers since the reset (state.cu), so they are not copied
-    const int rb = F / WF_CL, rr = F % WF_CL;
+    const int rb = F / CL, rr = F % CL;
     const int rows = rb + (rank < rr ? 1 : 0);
     const int r0 = rank * rb + (rank < rr ? rank : rr);
-    for (int c = warp; c < n_rem; c += WF_WARPS) {
+    for (int c = warp; c < n_rem; c += WARPS) {
       const double* __restrict__ src = Bcur + (size_t)idx_rem[c] * LDF + r0;
       double* __restrict__ dst = Bnext + (size_t)c * LDF + r0;
       for (int f = lane; f < rows; f += 32) dst[f] = src[f];
@@ -807,11 +828,35 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   if (rank == 0 && tid == 0) st.bd_sel[slot] = sel ^ 1;
 }
 
+// SNMFNAT_WSOLVE=c4 selects the one-CTA-per-SM geometry (4-CTA clusters, V staged in shared memory); the default is
+// the 8-CTA / two-CTAs-per-SM geometry
+static bool wsolve_use_c8() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SNMFNAT_WSOLVE");
+    v = (e && e[0] == 'c' && e[1] == '4') ? 0 : 1;
+  }
+  return v == 1;
+}
+static bool wsolve_geom_ok(const OnlineDims& d, int CL, int TPC) {
+  return (d.F + 7) / 8 <= CL * TPC + 1 && d.F / 8 <= CL * TPC;
+}
+
 bool wsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
   if (d.R_a > 64 || d.R_a < 1) return false;
-  if ((d.F + 7) / 8 > WF_CL * WF_TPC + 1 || d.F / 8 > WF_CL * WF_TPC) return false;
-  const size_t bytes = d.R_a <= 56 ? WfLayout<7>(d.m_a).bytes : WfLayout<8>(d.m_a).bytes;
+  if (!wsolve_geom_ok(d, 4, 16)) return false;   // both geometries cover 64 full tiles + 1 leftover
+  const size_t bytes = d.R_a <= 56 ? WfLayout<7, 4, 16, true>(d.m_a).bytes : WfLayout<8, 4, 16, true>(d.m_a).bytes;
   return (int)bytes <= ctx->max_smem_optin;
+}
+
+template <int KT, int CL, int TPC, bool VSMEM>
+static void launch_wsolve_variant(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                                  const TraceArrays& t, int has_trace, int n_active, int g_step, const double2* tab) {
+  const size_t smem = WfLayout<KT, CL, TPC, VSMEM>(d.m_a).bytes;
+  auto kern = wsolve_fast_kernel<KT, CL, TPC, VSMEM>;
+  SN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!VSMEM) SN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  kern<<<dim3(CL * n_active), dim3((TPC + 1) * 32), smem, ctx->stream>>>(d, sc, st, t, has_trace, g_step, tab);
 }
 
 void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
@@ -819,16 +864,14 @@ void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScala
   const double2* tab = log_table(ctx);
   TraceArrays t{};
   if (tr) t = *tr;
+  const bool c8 = wsolve_use_c8() && wsolve_geom_ok(d, 8, 8) &&
+                  2 * (WfLayout<8, 8, 8, false>(d.m_a).bytes + 1024) <= (size_t)ctx->max_smem_optin + 1024;
   if (d.R_a <= 56) {
-    const size_t smem = WfLayout<7>(d.m_a).bytes;
-    SN_CUDA(cudaFuncSetAttribute(wsolve_fast_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wsolve_fast_kernel<7><<<dim3(WF_CL * n_active), dim3(WF_THREADS), smem, ctx->stream>>>(d, sc, st, t, tr ? 1 : 0,
-                                                                                            g_step, tab);
+    if (c8) launch_wsolve_variant<7, 8, 8, false>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
+    else launch_wsolve_variant<7, 4, 16, true>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
   } else {
-    const size_t smem = WfLayout<8>(d.m_a).bytes;
-    SN_CUDA(cudaFuncSetAttribute(wsolve_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wsolve_fast_kernel<8><<<dim3(WF_CL * n_active), dim3(WF_THREADS), smem, ctx->stream>>>(d, sc, st, t, tr ? 1 : 0,
-                                                                                            g_step, tab);
+    if (c8) launch_wsolve_variant<8, 8, 8, false>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
+    else launch_wsolve_variant<8, 4, 16, true>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
   }
   count_launch(ctx);
   check_launch(ctx, "wsolve_fast_kernel");
