@@ -18,7 +18,7 @@
 #include <cstring>
 #include <memory>
 #include "common.cuh"
-#include "train_kernels.cuh"
+#include "train_kernels2.cuh"
 
 using namespace snmfnat;
 using namespace snmfnat::train;
@@ -76,6 +76,10 @@ struct snmfnat_train {
   DevBuf<float> dbg_h, dbg_w;  // diagnostics (SNMFNAT_TRAIN_DEBUG=1)
   int cur_h = 0, cur_w = 0;
   CUtensorMap mH128[2], mHk[2], mHm[2], mWk[2], mWm[2], mW128[2];
+  // second-generation kernels (train_kernels2.cuh): 256-row K-major tiles and 16-row MN-major slices
+  CUtensorMap mHk256[2], mHm16[2], mWk256[2], mWm16[2];
+  int v2 = 1;                 // SNMFNAT_TRAIN_V1=1 selects the first-generation kernels
+  int nblk_h = 0, nlast_h = 0, nblocks_w = 0;
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   double* h_scal = nullptr;  // pinned: [0] = div
@@ -268,7 +272,41 @@ size_t wphase_smem(const snmfnat_train* t) {
   return t->nc == 16 ? wphase_smem_bytes<16>(t->nkb, t->nst_w) : wphase_smem_bytes<32>(t->nkb, t->nst_w);
 }
 
+void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
+  HPhase2Args a;
+  a.F = t->F; a.Fm = t->tail_row >= 0 ? t->F - 1 : t->F; a.Kp = t->Kp; a.nkb = t->nkb;
+  a.nblk = t->nblk_h; a.nlast = t->nlast_h;
+  a.ntiles = t->ntiles;
+  a.update = update; a.want_cost = want_cost; a.tail_row = t->tail_row;
+  a.T = t->T; a.ldt = t->ldt;
+  a.Vt = t->Vt.p;
+  a.invden = t->invden[t->cur_w].p; a.wtail = t->wtail[t->cur_w].p;
+  a.hs_part = t->hs_part.p; a.gt_part = t->gt_part.p; a.cost_part = t->cost_part.p;
+  a.probe = (update && t->iters_done == 0 && t->dbg_h.p) ? 1 : 0;
+  const int ch = t->cur_h, cw = t->cur_w;
+  hphase2_kernel<<<t->grid_h, THREADS, phase2_smem_bytes(t->nkb), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1],
+                                                                                     t->mWk256[cw], t->mWm16[cw], a);
+  count_launch(t->ctx);
+  check_launch(t->ctx, "hphase2_kernel");
+}
+
+void launch_wphase2(snmfnat_train* t, int hbuf) {
+  WPhase2Args a;
+  a.F = t->F; a.Kp = t->Kp; a.nkb = t->nkb;
+  a.nchunk = t->nchunk; a.ngroups = t->ngroups; a.nblocks = t->nblocks_w; a.ldv = t->ldv; a.T = t->T;
+  a.V = t->V.p; a.Gpart = t->Gpart.p;
+  const int grid = t->nchunk * t->ngroups, cw = t->cur_w;
+  wphase2_kernel<<<grid, THREADS, phase2_smem_bytes(t->nkb), t->ctx->stream>>>(t->mW128[cw], t->mHk256[hbuf],
+                                                                                t->mHm16[hbuf], a);
+  count_launch(t->ctx);
+  check_launch(t->ctx, "wphase2_kernel");
+}
+
 void launch_hphase(snmfnat_train* t, int update, int want_cost) {
+  if (t->v2) {
+    launch_hphase2(t, update, want_cost);
+    return;
+  }
   HPhaseArgs a;
   a.F = t->F; a.Kp = t->Kp; a.nkb = t->nkb;
   a.nch = (t->F + t->nc - 1) / t->nc;
@@ -294,6 +332,10 @@ void launch_hphase(snmfnat_train* t, int update, int want_cost) {
 }
 
 void launch_wphase(snmfnat_train* t, int hbuf) {
+  if (t->v2) {
+    launch_wphase2(t, hbuf);
+    return;
+  }
   WPhaseArgs a;
   a.F = t->F; a.Kp = t->Kp; a.nkb = t->nkb;
   a.nchunk = t->nchunk; a.ngroups = t->ngroups; a.nstages = t->nstages; a.nst = t->nst_w; a.ldv = t->ldv; a.T = t->T;
@@ -400,6 +442,16 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
   t->ldt = (T_local + 3) / 4 * 4;
   t->grid_h = std::min(t->ntiles, ctx->sm_count);
   t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nstages));
+  t->v2 = (getenv("SNMFNAT_TRAIN_V1") == nullptr && phase2_smem_bytes(t->nkb) <= (size_t)ctx->max_smem_optin) ? 1 : 0;
+  if (t->v2) {
+    const int Fm = t->tail_row >= 0 ? F - 1 : F;
+    t->nblk_h = (Fm + NB - 1) / NB;
+    t->nlast_h = (Fm - (t->nblk_h - 1) * NB + 15) / 16 * 16;
+    t->nblocks_w = (int)((T_local + NB - 1) / NB);
+    t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nblocks_w));
+    SN_CUDA(cudaFuncSetAttribute(hphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb)));
+    SN_CUDA(cudaFuncSetAttribute(wphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb)));
+  }
   SN_REQUIRE(hphase_smem(t.get()) <= (size_t)ctx->max_smem_optin && wphase_smem(t.get()) <= (size_t)ctx->max_smem_optin,
              SNMFNAT_EUNSUPPORTED, "shared memory: need %zu / %zu bytes, device offers %d", hphase_smem(t.get()),
              wphase_smem(t.get()), ctx->max_smem_optin);
@@ -452,6 +504,10 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
     make_map(&t->mWk[i], t->Wt[i].p, t->Kp, F, pitch, t->nc);
     make_map(&t->mWm[i], t->Wt[i].p, t->Kp, F, pitch, t->nc, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     make_map(&t->mW128[i], t->Wt[i].p, t->Kp, F, pitch, BM);
+    make_map(&t->mHk256[i], t->H[i].p, t->Kp, T_local, pitch, NB);
+    make_map(&t->mHm16[i], t->H[i].p, t->Kp, T_local, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    make_map(&t->mWk256[i], t->Wt[i].p, t->Kp, F, pitch, NB);
+    make_map(&t->mWm16[i], t->Wt[i].p, t->Kp, F, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   }
   SN_CUDA(cudaStreamSynchronize(st));
   *out = t.release();

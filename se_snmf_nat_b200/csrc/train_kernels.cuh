@@ -183,14 +183,21 @@ hphase_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ 
       const uint32_t hs_a = smem_u32(Hs), wk_a = smem_u32(Wk), wm_a = smem_u32(Wm);
       uint32_t n = 0;
       int it = 0;
+      const bool probe = a.dbg && blockIdx.x == 0;
+      long long p_h = 0, p_ws = 0, p_i1 = 0, p_r = 0, p_i2 = 0, p_t0 = clock64();
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        long long q0 = clock64();
         mbar_wait(h_full, it & 1);
+        p_h += clock64() - q0;
         tc_fence_after();
         const uint32_t nbase = n;
         for (int c = 0; c <= nch; ++c) {
           if (c < nch) {  // Lambda(c) = H_tile * W_chunk(c)'
             const uint32_t m = nbase + c, s = m % nst, b = m & 1;
+            q0 = clock64();
             mbar_wait(ws_full + s, (m / nst) & 1);
+            p_ws += clock64() - q0;
+            q0 = clock64();
             tc_fence_after();
             const uint32_t d = tmem + LAM_COL + NC * b;
             const uint32_t id = (c == nch - 1) ? id1l : id1;
@@ -200,10 +207,14 @@ hphase_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ 
               mma_ss(d, da, db, id, k > 0);
             }
             mma_commit(lam_full + b);
+            p_i1 += clock64() - q0;
           }
           if (c >= 1) {  // Num += R(c-1) * W_chunk(c-1)
             const uint32_t m = nbase + c - 1, s = m % nst, b = m & 1;
+            q0 = clock64();
             mbar_wait(r_full + b, (m >> 1) & 1);
+            p_r += clock64() - q0;
+            q0 = clock64();
             tc_fence_after();
             if (upd) {
               if (c == 1) {
@@ -220,10 +231,15 @@ hphase_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ 
             } else {
               mbar_arrive(ws_empty + s);
             }
+            p_i2 += clock64() - q0;
           }
         }
         n = nbase + nch;
       }
+      if (probe)
+        printf("hphase probe (MMA issuer, CTA 0): total %lld clk, %d tiles x %d chunks, nst %d | wait h_full %lld, wait ws_full %lld, "
+               "issue MMA1 %lld, wait r_full %lld, issue MMA2 %lld\n",
+               clock64() - p_t0, it, nch, nst, p_h, p_ws, p_i1, p_r, p_i2);
     }
   } else {
     // ===================================================================== epilogue: two groups of 128 threads

@@ -1,0 +1,611 @@
+// Second generation of the dictionary-training kernels (same math and same roles as train_kernels.cuh).
+//
+// What changed, and why (measured on B200, profiles/r01_train_*): with both operands in shared memory a tcgen05.mma
+// of M = 128 reads its A operand at one 128-byte row per clock, i.e. ~128 clk per instruction whatever N is, while the
+// tensor pipe itself needs N/2 clk.  The first-generation kernels streamed the other matrix in 16-row chunks, so the
+// first product (Lambda = A * chunk') ran with N = 16: 97 clk per instruction measured, 6-9 % of the tensor pipe.
+// Here the first product is issued with N = 256:
+//   * Lambda block [128 x 256] = A_tile [128 x Kp] * X_block' with X_block = 256 rows of the streamed matrix, delivered
+//     as K-major tiles [256 rows x 32 atoms] (32 KB, 2-stage ring): every instruction is M128 x N256 x K8, A-read time
+//     == tensor time.
+//   * the epilogue warps turn the whole 256-column Lambda block into R = V ./ Lambda in place in tensor memory
+//     (V prefetched from HBM while the MMAs run),
+//   * the second product Acc += R * X_block reads R from tensor memory and X_block as MN-major 16-row slices (as before).
+// Tensor memory: accumulator (Kp <= 256 columns) + one Lambda block (256 columns) = 512 columns.
+// In the H phase the Nyquist bin (F % 128 == 1) stays off the tensor cores: its Lambda is a dot product per frame in
+// the epilogue and its contribution to the numerator a rank-1 term of the H update.
+#pragma once
+#include "train_kernels.cuh"
+
+namespace snmfnat {
+namespace train {
+
+constexpr int NB = 256;        // columns of one Lambda block (N of the first product)
+constexpr int SL = 16;         // rows of one MN-major slice of the second product
+constexpr int NSTA = 2;        // ring of K-major tiles [256 x 128 B]
+constexpr int NSTB = 2;        // ring of MN-major slices [nkb][16 x 128 B]
+constexpr int KTILE_BYTES = NB * 128;
+
+struct HPhase2Args {
+  int F, Fm, Kp, nkb;  // bins, bins that go through the tensor cores, padded rank, Kp/32
+  int nblk, nlast;     // 256-bin blocks, N of the last block (multiple of 16)
+  int ntiles;
+  int update, want_cost;
+  int tail_row;        // F-1 when that bin is handled by the epilogue (F % 128 == 1), else -1
+  long long T, ldt;
+  const float* Vt;      // [F][ldt]
+  const float* invden;  // [Kp]
+  const float* wtail;   // [Kp] W(tail_row, :)
+  float* hs_part;       // [grid][Kp]
+  float* gt_part;       // [grid][Kp]
+  double* cost_part;    // [grid]
+  int probe;            // print the MMA issuer's wait/issue clocks of CTA 0 (diagnostics)
+};
+
+struct WPhase2Args {
+  int F, Kp, nkb;
+  int nchunk, ngroups;  // 128-bin chunks; frame groups (grid = nchunk * ngroups)
+  int nblocks;          // ceil(T / 256)
+  int ldv;
+  long long T;
+  const float* V;       // [T][ldv]
+  float* Gpart;         // [ngroups][nchunk*128][Kp]
+};
+
+__host__ __device__ constexpr size_t phase2_smem_bytes(int nkb) {
+  return (size_t)nkb * 16384 + (size_t)NSTA * KTILE_BYTES + (size_t)NSTB * nkb * SL * 128 + 2 * BM * 4 + 64 + 32 * 8 + 1024;
+}
+
+// ------------------------------------------------------------------------------------------------ H phase
+__global__ void __launch_bounds__(THREADS, 1)
+hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapHout,
+               const __grid_constant__ CUtensorMap mapWk, const __grid_constant__ CUtensorMap mapWm, const HPhase2Args a) {
+  using namespace umma;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int nkb = a.nkb, Kp = a.Kp, nblk = a.nblk;
+  const int sliceb = nkb * SL * 128;                      // bytes of one MN-major slice (all column blocks)
+  uint8_t* Hs = smem;                                     // nkb x [128 x 128 B]                 SW128, A of product 1
+  uint8_t* Ak = Hs + nkb * 16384;                         // NSTA x [256 x 128 B]                SW128 (K-major)
+  uint8_t* Bm = Ak + NSTA * KTILE_BYTES;                  // NSTB x nkb x [16 x 128 B]           SW128_ATOM_32B
+  float* vtail_s = (float*)(Bm + NSTB * sliceb);          // [128]
+  float* dotp = vtail_s + BM;                             // [128]
+  double* red = (double*)(dotp + BM);                     // [8]
+  uint64_t* bars = (uint64_t*)(red + 8);
+  uint64_t* h_full = bars + 0;
+  uint64_t* h_empty = bars + 1;
+  uint64_t* num_full = bars + 2;
+  uint64_t* num_empty = bars + 3;
+  uint64_t* lam_full = bars + 4;
+  uint64_t* r_full = bars + 5;
+  uint64_t* a_full = bars + 6;                   // [NSTA]
+  uint64_t* a_empty = bars + 6 + NSTA;           // [NSTA]
+  uint64_t* b_full = bars + 6 + 2 * NSTA;        // [NSTB]
+  uint64_t* b_empty = bars + 6 + 2 * NSTA + NSTB;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * NSTA + 2 * NSTB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(h_full, 1);
+    mbar_init(h_empty, 1);
+    mbar_init(num_full, 1);
+    mbar_init(num_empty, 2 * BM);
+    mbar_init(lam_full, 1);
+    mbar_init(r_full, 2 * BM);
+    for (int i = 0; i < NSTA; ++i) {
+      mbar_init(a_full + i, 1);
+      mbar_init(a_empty + i, 1);
+    }
+    for (int i = 0; i < NSTB; ++i) {
+      mbar_init(b_full + i, 1);
+      mbar_init(b_empty + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool upd = a.update != 0;
+  const int my_tiles = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0 && my_tiles > 0) {
+      tma_prefetch_desc(&mapH);
+      tma_prefetch_desc(&mapWk);
+      tma_prefetch_desc(&mapWm);
+      uint32_t ga = 0, gb = 0;
+      auto load_k = [&](int b, int ks) {
+        const uint32_t s = ga % NSTA;
+        mbar_wait(a_empty + s, ((ga / NSTA) & 1) ^ 1);
+        mbar_expect_tx(a_full + s, KTILE_BYTES);
+        tma_load_2d(Ak + s * KTILE_BYTES, &mapWk, a_full + s, ks * KB, b * NB);
+        ++ga;
+      };
+      auto load_s = [&](int b, int js) {
+        const uint32_t s = gb % NSTB;
+        mbar_wait(b_empty + s, ((gb / NSTB) & 1) ^ 1);
+        mbar_expect_tx(b_full + s, sliceb);
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(Bm + s * sliceb + kb * SL * 128, &mapWm, b_full + s, kb * KB, b * NB + js * SL);
+        ++gb;
+      };
+      // the first PRE K-major tiles of a block are requested while the previous block is still in its second product
+      // (the dictionary does not depend on the frame tile, so this also runs across tile boundaries)
+      const int PRE = nkb < NSTA ? nkb : NSTA;
+      for (int ks = 0; ks < PRE; ++ks) load_k(0, ks);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        const int t0 = tile * BM;
+        mbar_wait(h_empty, (it & 1) ^ 1);
+        mbar_expect_tx(h_full, nkb * 16384);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Hs + kb * 16384, &mapH, h_full, kb * KB, t0);
+        for (int b = 0; b < nblk; ++b) {
+          for (int ks = PRE; ks < nkb; ++ks) load_k(b, ks);
+          const int Nb = (b == nblk - 1) ? a.nlast : NB;
+          const int nsl = upd ? Nb / SL : 0;
+          const bool has_next = (b + 1 < nblk) || (it + 1 < my_tiles);
+          const int nb = (b + 1 < nblk) ? b + 1 : 0;
+          bool pre_done = false;
+          for (int js = 0; js < nsl; ++js) {
+            load_s(b, js);
+            if (!pre_done && (js == 1 || js == nsl - 1)) {
+              if (has_next)
+                for (int ks = 0; ks < PRE; ++ks) load_k(nb, ks);
+              pre_done = true;
+            }
+          }
+          if (!pre_done && has_next)
+            for (int ks = 0; ks < PRE; ++ks) load_k(nb, ks);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0 && my_tiles > 0) {
+      const uint32_t id2 = idesc_tf32(BM, Kp, 0, 1);
+      const uint32_t hs_a = smem_u32(Hs), ak_a = smem_u32(Ak), bm_a = smem_u32(Bm);
+      uint32_t ga = 0, gb = 0, g = 0;
+      int it = 0;
+      long long p_h = 0, p_a = 0, p_i1 = 0, p_r = 0, p_i2 = 0, p_t0 = clock64();
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        long long q0 = clock64();
+        mbar_wait(h_full, it & 1);
+        p_h += clock64() - q0;
+        tc_fence_after();
+        for (int b = 0; b < nblk; ++b, ++g) {
+          const int Nb = (b == nblk - 1) ? a.nlast : NB;
+          const uint32_t id1 = idesc_tf32(BM, Nb, 0, 0);
+          // Lambda block = H_tile * W_block'
+          for (int ks = 0; ks < nkb; ++ks, ++ga) {
+            const uint32_t s = ga % NSTA;
+            q0 = clock64();
+            mbar_wait(a_full + s, (ga / NSTA) & 1);
+            p_a += clock64() - q0;
+            q0 = clock64();
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = smem_desc(hs_a + ks * 16384 + kk * 32, 16, 1024);
+              const uint64_t db = smem_desc(ak_a + s * KTILE_BYTES + kk * 32, 16, 1024);
+              mma_ss(tmem + LAM_COL, da, db, id1, (ks > 0) || (kk > 0));
+            }
+            mma_commit(a_empty + s);
+            p_i1 += clock64() - q0;
+          }
+          mma_commit(lam_full);
+          q0 = clock64();
+          mbar_wait(r_full, g & 1);
+          p_r += clock64() - q0;
+          tc_fence_after();
+          if (upd) {
+            if (b == 0) {
+              mbar_wait(num_empty, (it & 1) ^ 1);
+              tc_fence_after();
+            }
+            // Num += R block * W_block
+            q0 = clock64();
+            for (int js = 0; js < Nb / SL; ++js, ++gb) {
+              const uint32_t s = gb % NSTB;
+              mbar_wait(b_full + s, (gb / NSTB) & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int j = 0; j < SL / 8; ++j) {
+                const uint64_t db = smem_desc(bm_a + s * sliceb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
+                mma_ts(tmem, tmem + LAM_COL + SL * js + 8 * j, db, id2, (b > 0) || (js > 0) || (j > 0));
+              }
+              mma_commit(b_empty + s);
+            }
+            if (b == nblk - 1) mma_commit(num_full);
+            p_i2 += clock64() - q0;
+          }
+        }
+      }
+      if (a.probe && blockIdx.x == 0)
+        printf("hphase2 probe (MMA issuer, CTA 0): total %lld clk, %d tiles x %d blocks | wait h_full %lld, wait K tiles %lld, "
+               "issue MMA1 %lld, wait r_full %lld, MMA2 (issue + slice waits) %lld\n",
+               clock64() - p_t0, it, nblk, p_h, p_a, p_i1, p_r, p_i2);
+    }
+  } else {
+    // ===================================================================== epilogue: two groups of 128 threads
+    const int e = (warp - 2) >> 2;           // group: columns [128 e, 128 e + 128) of a Lambda block
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = 32 * q + lane;           // frame inside the tile
+    const int etid = (warp - 2) * 32 + lane; // 0..255
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    float hs_acc = 0.f, gt_acc = 0.f;
+    double cost_acc = 0.0;
+    uint32_t g = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const long long t0 = (long long)tile * BM;
+      const bool row_ok = (t0 + row) < a.T;
+      const float* vcol = a.Vt + t0 + row;
+      float cost_tile = 0.f;
+      auto load_v = [&](int f0, float (&dst)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = (row_ok && f0 + j < a.Fm) ? __ldg(vcol + (size_t)(f0 + j) * a.ldt) : 0.f;
+      };
+      for (int b = 0; b < nblk; ++b, ++g) {
+        const int Nb = (b == nblk - 1) ? a.nlast : NB;
+        const int c_lo = 128 * e;
+        float vn[32];
+        if (c_lo < Nb) load_v(b * NB + c_lo, vn);          // in flight while the first product runs
+        mbar_wait(lam_full, g & 1);
+        tc_fence_after();
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = c_lo + 32 * cc;
+          if (c0 >= Nb) break;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = vn[j];
+          if (cc + 1 < 4 && c0 + 32 < Nb) load_v(b * NB + c0 + 32, vn);
+          uint32_t lam[32];
+          tmem_ld32(lane_addr + LAM_COL + c0, lam);
+          tmem_wait_ld();
+          const int f0 = b * NB + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = row_ok && (f0 + j < a.Fm);
+            const float vv = fmaxf(v[j], FLRF);                     // sparse_nmf.m:169
+            const float ll = fmaxf(__uint_as_float(lam[j]), FLRF);  // :167,208
+            const float r = __fdividef(vv, ll);
+            lam[j] = ok ? to_tf32_rn(r) : 0u;
+            if (a.want_cost && ok) cost_tile += vv * __logf(r) - vv + ll;  // :250
+          }
+          if (upd) tmem_st32(lane_addr + LAM_COL + c0, lam);
+        }
+        if (upd) tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(r_full);
+      }
+      // ---- the bin that stays off the tensor cores: Lambda(tail, frame) = W(tail,:) * h (state before the update)
+      mbar_wait(h_full, it & 1);
+      float r_t = 0.f;
+      if (a.tail_row >= 0) {
+        float d0 = 0.f;
+        for (int kb = e; kb < nkb; kb += 2) {
+          const uint8_t* hrow = Hs + kb * 16384 + row * 128;
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const float4 hv = *(const float4*)(hrow + (((g4 ^ row) & 7) << 4));
+            const float4 wt = __ldg((const float4*)(a.wtail + kb * KB + 4 * g4));
+            d0 += wt.x * h_unbias(hv.x) + wt.y * h_unbias(hv.y) + wt.z * h_unbias(hv.z) + wt.w * h_unbias(hv.w);
+          }
+        }
+        (e == 0 ? vtail_s : dotp)[row] = d0;
+        named_bar_sync(1, 2 * BM);
+        const float lam_t = fmaxf(vtail_s[row] + dotp[row], FLRF);
+        const float vv = fmaxf(row_ok ? __ldg(a.Vt + (size_t)a.tail_row * a.ldt + t0 + row) : 0.f, FLRF);
+        r_t = row_ok ? __fdividef(vv, lam_t) : 0.f;
+        if (a.want_cost && row_ok && e == 0) cost_tile += vv * __logf(r_t) - vv + lam_t;
+        named_bar_sync(1, 2 * BM);
+        if (e == 0) vtail_s[row] = vv;
+        r_t = __uint_as_float(to_tf32_rn(r_t));
+      }
+      cost_acc += (double)cost_tile;
+      if (upd) {
+        // ---- H' = H .* Num ./ dph  (sparse_nmf.m:192-195), in place in the shared-memory tile
+        mbar_wait(num_full, it & 1);
+        tc_fence_after();
+        float dot = 0.f;
+        for (int kb = e; kb < nkb; kb += 2) {
+          uint32_t num[32];
+          tmem_ld32(lane_addr + kb * KB, num);
+          uint8_t* hrow = Hs + kb * 16384 + row * 128;
+          float4 hv[8];
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) hv[g4] = *(const float4*)(hrow + (((g4 ^ row) & 7) << 4));
+          tmem_wait_ld();
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            hv[g4].x = row_ok ? h_unbias(hv[g4].x) : 0.f;
+            hv[g4].y = row_ok ? h_unbias(hv[g4].y) : 0.f;
+            hv[g4].z = row_ok ? h_unbias(hv[g4].z) : 0.f;
+            hv[g4].w = row_ok ? h_unbias(hv[g4].w) : 0.f;
+          }
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const int k = kb * KB + 4 * g4;
+            const float4 id = __ldg((const float4*)(a.invden + k));
+            const float4 wt = __ldg((const float4*)(a.wtail + k));
+            float4 x = hv[g4];
+            x.x = x.x * (__uint_as_float(num[4 * g4 + 0]) + r_t * wt.x) * id.x;
+            x.y = x.y * (__uint_as_float(num[4 * g4 + 1]) + r_t * wt.y) * id.y;
+            x.z = x.z * (__uint_as_float(num[4 * g4 + 2]) + r_t * wt.z) * id.z;
+            x.w = x.w * (__uint_as_float(num[4 * g4 + 3]) + r_t * wt.w) * id.w;
+            dot += wt.x * x.x + wt.y * x.y + wt.z * x.z + wt.w * x.w;
+            x.x = h_bias(x.x); x.y = h_bias(x.y); x.z = h_bias(x.z); x.w = h_bias(x.w);
+            *(float4*)(hrow + (((g4 ^ row) & 7) << 4)) = x;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(num_empty);
+        fence_proxy_async();
+        if (e == 1) dotp[row] = dot;
+        named_bar_sync(1, 2 * BM);
+        if (e == 0) {
+          float rt = 0.f;
+          if (a.tail_row >= 0 && row_ok) rt = __fdividef(vtail_s[row], fmaxf(dot + dotp[row], FLRF));
+          dotp[row] = rt;
+        }
+        named_bar_sync(1, 2 * BM);
+        if (etid == 0) {
+          for (int kb = 0; kb < nkb; ++kb) tma_store_2d(&mapHout, Hs + kb * 16384, kb * KB, (int)t0);
+          tma_store_commit();
+        }
+        // ---- column pass over the tile: sum(H',2) and the tail row of (V./Lambda') * H''
+        if (etid < Kp) {
+          const uint8_t* col = Hs + (etid >> 5) * 16384;
+          const uint32_t j = etid & 31;
+          float s1 = 0.f, s2 = 0.f;
+          const int nrows = (int)((a.T - t0 < BM) ? (a.T - t0) : BM);
+#pragma unroll 4
+          for (int r = 0; r < nrows; ++r) {
+            const float hval = h_unbias(*(const float*)(col + sw128_off(r, j)));
+            s1 += hval;
+            s2 += dotp[r] * hval;
+          }
+          hs_acc += s1;
+          gt_acc += s2;
+        }
+        named_bar_sync(1, 2 * BM);
+        if (etid == 0) {
+          tma_store_wait_read();
+          mbar_arrive(h_empty);
+        }
+      } else {
+        named_bar_sync(1, 2 * BM);
+        if (etid == 0) mbar_arrive(h_empty);
+      }
+    }
+    if (etid == 0) tma_store_wait_all();
+    if (etid < Kp) {
+      a.hs_part[(size_t)blockIdx.x * Kp + etid] = hs_acc;
+      a.gt_part[(size_t)blockIdx.x * Kp + etid] = gt_acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
+    if (lane == 0) red[warp - 2] = cost_acc;
+    named_bar_sync(1, 2 * BM);
+    if (etid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      a.cost_part[blockIdx.x] = t;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ W phase
+__global__ void __launch_bounds__(THREADS, 1)
+wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapHk,
+               const __grid_constant__ CUtensorMap mapHm, const WPhase2Args a) {
+  using namespace umma;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int nkb = a.nkb, Kp = a.Kp;
+  const int sliceb = nkb * SL * 128;
+  uint8_t* Wc = smem;                                  // nkb x [128 x 128 B]   resident dictionary rows
+  uint8_t* Ak = Wc + nkb * 16384;                      // NSTA x [256 x 128 B]  K-major tiles of H'
+  uint8_t* Bm = Ak + NSTA * KTILE_BYTES;               // NSTB x nkb x [16 x 128 B]  MN-major slices of H'
+  uint64_t* bars = (uint64_t*)(Bm + NSTB * sliceb);
+  uint64_t* wc_full = bars + 0;
+  uint64_t* g_full = bars + 1;
+  uint64_t* lam_full = bars + 2;
+  uint64_t* r_full = bars + 3;
+  uint64_t* a_full = bars + 4;
+  uint64_t* a_empty = bars + 4 + NSTA;
+  uint64_t* b_full = bars + 4 + 2 * NSTA;
+  uint64_t* b_empty = bars + 4 + 2 * NSTA + NSTB;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4 + 2 * NSTA + 2 * NSTB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(wc_full, 1);
+    mbar_init(g_full, 1);
+    mbar_init(lam_full, 1);
+    mbar_init(r_full, 2 * BM);
+    for (int i = 0; i < NSTA; ++i) {
+      mbar_init(a_full + i, 1);
+      mbar_init(a_empty + i, 1);
+    }
+    for (int i = 0; i < NSTB; ++i) {
+      mbar_init(b_full + i, 1);
+      mbar_init(b_empty + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int chunk = blockIdx.x % a.nchunk, grp = blockIdx.x / a.nchunk;
+  const int n_my = (a.nblocks > grp) ? (a.nblocks - grp + a.ngroups - 1) / a.ngroups : 0;
+  // N of block i of this CTA (frames beyond T read as zero rows; N stays a multiple of 16)
+  auto block_n = [&](int i) {
+    const long long t0 = (long long)(grp + i * a.ngroups) * NB;
+    const long long left = a.T - t0;
+    return left >= NB ? NB : (int)((left + 15) / 16 * 16);
+  };
+
+  if (warp == 0) {
+    if (lane == 0 && n_my > 0) {
+      tma_prefetch_desc(&mapW);
+      tma_prefetch_desc(&mapHk);
+      tma_prefetch_desc(&mapHm);
+      mbar_expect_tx(wc_full, nkb * 16384);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Wc + kb * 16384, &mapW, wc_full, kb * KB, chunk * BM);
+      uint32_t ga = 0, gb = 0;
+      auto load_k = [&](int i, int ks) {
+        const uint32_t s = ga % NSTA;
+        mbar_wait(a_empty + s, ((ga / NSTA) & 1) ^ 1);
+        mbar_expect_tx(a_full + s, KTILE_BYTES);
+        tma_load_2d(Ak + s * KTILE_BYTES, &mapHk, a_full + s, ks * KB, (grp + i * a.ngroups) * NB);
+        ++ga;
+      };
+      auto load_s = [&](int i, int js) {
+        const uint32_t s = gb % NSTB;
+        mbar_wait(b_empty + s, ((gb / NSTB) & 1) ^ 1);
+        mbar_expect_tx(b_full + s, sliceb);
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(Bm + s * sliceb + kb * SL * 128, &mapHm, b_full + s, kb * KB, (grp + i * a.ngroups) * NB + js * SL);
+        ++gb;
+      };
+      const int PRE = nkb < NSTA ? nkb : NSTA;
+      for (int ks = 0; ks < PRE; ++ks) load_k(0, ks);
+      for (int i = 0; i < n_my; ++i) {
+        for (int ks = PRE; ks < nkb; ++ks) load_k(i, ks);
+        const int nsl = block_n(i) / SL;
+        const bool has_next = i + 1 < n_my;
+        bool pre_done = false;
+        for (int js = 0; js < nsl; ++js) {
+          load_s(i, js);
+          if (!pre_done && (js == 1 || js == nsl - 1)) {
+            if (has_next)
+              for (int ks = 0; ks < PRE; ++ks) load_k(i + 1, ks);
+            pre_done = true;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_my > 0) {
+      const uint32_t id4 = idesc_tf32(BM, Kp, 0, 1);
+      const uint32_t wc_a = smem_u32(Wc), ak_a = smem_u32(Ak), bm_a = smem_u32(Bm);
+      mbar_wait(wc_full, 0);
+      tc_fence_after();
+      uint32_t ga = 0, gb = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int Nb = block_n(i);
+        const uint32_t id3 = idesc_tf32(BM, Nb, 0, 0);
+        // Lambda block = W_rows * H'_block'
+        for (int ks = 0; ks < nkb; ++ks, ++ga) {
+          const uint32_t s = ga % NSTA;
+          mbar_wait(a_full + s, (ga / NSTA) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = smem_desc(wc_a + ks * 16384 + kk * 32, 16, 1024);
+            const uint64_t db = smem_desc(ak_a + s * KTILE_BYTES + kk * 32, 16, 1024);
+            mma_ss(tmem + LAM_COL, da, db, id3, (ks > 0) || (kk > 0));
+          }
+          mma_commit(a_empty + s);
+        }
+        mma_commit(lam_full);
+        mbar_wait(r_full, i & 1);
+        tc_fence_after();
+        // G += R block * H'_block
+        for (int js = 0; js < Nb / SL; ++js, ++gb) {
+          const uint32_t s = gb % NSTB;
+          mbar_wait(b_full + s, (gb / NSTB) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < SL / 8; ++j) {
+            const uint64_t db = smem_desc(bm_a + s * sliceb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
+            mma_ts(tmem, tmem + LAM_COL + SL * js + 8 * j, db, id4, (i > 0) || (js > 0) || (j > 0));
+          }
+          mma_commit(b_empty + s);
+        }
+        if (i == n_my - 1) mma_commit(g_full);
+      }
+    }
+  } else {
+    const int e = (warp - 2) >> 2, q = warp & 3;
+    const int row = 32 * q + lane;
+    const int f = chunk * BM + row;
+    const bool f_ok = f < a.F;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    for (int i = 0; i < n_my; ++i) {
+      const int Nb = block_n(i);
+      const long long tb = (long long)(grp + i * a.ngroups) * NB;
+      const int c_lo = 128 * e;
+      auto load_v = [&](int c0, float (&dst)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          dst[j] = (f_ok && tb + c0 + j < a.T) ? __ldg(a.V + (size_t)(tb + c0 + j) * a.ldv + f) : 0.f;
+      };
+      float vn[32];
+      if (c_lo < Nb) load_v(c_lo, vn);
+      mbar_wait(lam_full, i & 1);
+      tc_fence_after();
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = c_lo + 32 * cc;
+        if (c0 >= Nb) break;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = vn[j];
+        if (cc + 1 < 4 && c0 + 32 < Nb) load_v(c0 + 32, vn);
+        uint32_t lam[32];
+        tmem_ld32(lane_addr + LAM_COL + c0, lam);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = f_ok && (tb + c0 + j < a.T);
+          const float r = __fdividef(fmaxf(v[j], FLRF), fmaxf(__uint_as_float(lam[j]), FLRF));
+          lam[j] = ok ? to_tf32_rn(r) : 0u;
+        }
+        tmem_st32(lane_addr + LAM_COL + c0, lam);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(r_full);
+    }
+    // ---- G tile -> this group's partial in HBM
+    float* gout = a.Gpart + ((size_t)grp * a.nchunk * BM + (size_t)chunk * BM + row) * Kp;
+    if (n_my > 0) {
+      mbar_wait(g_full, 0);
+      tc_fence_after();
+    }
+    for (int kb = e; kb < nkb; kb += 2) {
+      uint32_t g[32];
+      if (n_my > 0) {
+        tmem_ld32(lane_addr + kb * KB, g);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = 0u;
+      }
+#pragma unroll
+      for (int g4 = 0; g4 < 8; ++g4)
+        *(uint4*)(gout + kb * KB + 4 * g4) = make_uint4(g[4 * g4], g[4 * g4 + 1], g[4 * g4 + 2], g[4 * g4 + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+}  // namespace train
+}  // namespace snmfnat
