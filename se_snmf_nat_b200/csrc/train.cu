@@ -79,7 +79,7 @@ struct snmfnat_train {
   // second-generation kernels (train_kernels2.cuh): 256-row K-major tiles and 16-row MN-major slices
   CUtensorMap mHk256[2], mHm16[2], mWk256[2], mWm16[2];
   int v2 = 1;                 // SNMFNAT_TRAIN_V1=1 selects the first-generation kernels
-  int nblk_h = 0, nlast_h = 0, nblocks_w = 0;
+  int nblk_h = 0, nlast_h = 0, nblocks_w = 0, nu = 2;
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   double* h_scal = nullptr;  // pinned: [0] = div
@@ -283,8 +283,9 @@ void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
   a.invden = t->invden[t->cur_w].p; a.wtail = t->wtail[t->cur_w].p;
   a.hs_part = t->hs_part.p; a.gt_part = t->gt_part.p; a.cost_part = t->cost_part.p;
   a.probe = (update && t->iters_done == 0 && t->dbg_h.p) ? 1 : 0;
+  a.nu = t->nu;
   const int ch = t->cur_h, cw = t->cur_w;
-  hphase2_kernel<<<t->grid_h, THREADS, phase2_smem_bytes(t->nkb), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1],
+  hphase2_kernel<<<t->grid_h, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1],
                                                                                      t->mWk256[cw], t->mWm16[cw], a);
   count_launch(t->ctx);
   check_launch(t->ctx, "hphase2_kernel");
@@ -295,8 +296,9 @@ void launch_wphase2(snmfnat_train* t, int hbuf) {
   a.F = t->F; a.Kp = t->Kp; a.nkb = t->nkb;
   a.nchunk = t->nchunk; a.ngroups = t->ngroups; a.nblocks = t->nblocks_w; a.ldv = t->ldv; a.T = t->T;
   a.V = t->V.p; a.Gpart = t->Gpart.p;
+  a.nu = t->nu;
   const int grid = t->nchunk * t->ngroups, cw = t->cur_w;
-  wphase2_kernel<<<grid, THREADS, phase2_smem_bytes(t->nkb), t->ctx->stream>>>(t->mW128[cw], t->mHk256[hbuf],
+  wphase2_kernel<<<grid, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mW128[cw], t->mHk256[hbuf],
                                                                                 t->mHm16[hbuf], a);
   count_launch(t->ctx);
   check_launch(t->ctx, "wphase2_kernel");
@@ -442,15 +444,16 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
   t->ldt = (T_local + 3) / 4 * 4;
   t->grid_h = std::min(t->ntiles, ctx->sm_count);
   t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nstages));
-  t->v2 = (getenv("SNMFNAT_TRAIN_V1") == nullptr && phase2_smem_bytes(t->nkb) <= (size_t)ctx->max_smem_optin) ? 1 : 0;
+  t->nu = phase2_units(t->nkb, (size_t)ctx->max_smem_optin);
+  t->v2 = (getenv("SNMFNAT_TRAIN_V1") == nullptr && phase2_smem_bytes(t->nkb, t->nu) <= (size_t)ctx->max_smem_optin) ? 1 : 0;
   if (t->v2) {
     const int Fm = t->tail_row >= 0 ? F - 1 : F;
     t->nblk_h = (Fm + NB - 1) / NB;
     t->nlast_h = (Fm - (t->nblk_h - 1) * NB + 15) / 16 * 16;
     t->nblocks_w = (int)((T_local + NB - 1) / NB);
     t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nblocks_w));
-    SN_CUDA(cudaFuncSetAttribute(hphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb)));
-    SN_CUDA(cudaFuncSetAttribute(wphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb)));
+    SN_CUDA(cudaFuncSetAttribute(hphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
+    SN_CUDA(cudaFuncSetAttribute(wphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
   }
   SN_REQUIRE(hphase_smem(t.get()) <= (size_t)ctx->max_smem_optin && wphase_smem(t.get()) <= (size_t)ctx->max_smem_optin,
              SNMFNAT_EUNSUPPORTED, "shared memory: need %zu / %zu bytes, device offers %d", hphase_smem(t.get()),

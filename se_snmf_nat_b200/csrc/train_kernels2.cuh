@@ -6,8 +6,7 @@
 // first product (Lambda = A * chunk') ran with N = 16: 97 clk per instruction measured, 6-9 % of the tensor pipe.
 // Here the first product is issued with N = 256:
 //   * Lambda block [128 x 256] = A_tile [128 x Kp] * X_block' with X_block = 256 rows of the streamed matrix, delivered
-//     as K-major tiles [256 rows x 32 atoms] (32 KB, 2-stage ring): every instruction is M128 x N256 x K8, A-read time
-//     == tensor time.
+//     as K-major tiles [256 rows x 32 atoms] (32 KB): every instruction is M128 x N256 x K8, A-read time == tensor time.
 //   * the epilogue warps turn the whole 256-column Lambda block into R = V ./ Lambda in place in tensor memory
 //     (V prefetched from HBM while the MMAs run),
 //   * the second product Acc += R * X_block reads R from tensor memory and X_block as MN-major 16-row slices (as before).
@@ -22,9 +21,12 @@ namespace train {
 
 constexpr int NB = 256;        // columns of one Lambda block (N of the first product)
 constexpr int SL = 16;         // rows of one MN-major slice of the second product
-constexpr int NSTA = 2;        // ring of K-major tiles [256 x 128 B]
-constexpr int NSTB = 2;        // ring of MN-major slices [nkb][16 x 128 B]
 constexpr int KTILE_BYTES = NB * 128;
+// One ring of 16 KB units feeds both products in consumption order (K-major tile = 2 units, MN-major slice = 1 unit),
+// so whatever shared memory is left beside the resident tile is in flight for the product that is running: the
+// loads are latency-bound (bytes in flight / L2 latency), not bandwidth-bound.
+constexpr int UNIT = 16384;
+constexpr int NU_MAX = 8;
 
 struct HPhase2Args {
   int F, Fm, Kp, nkb;  // bins, bins that go through the tensor cores, padded rank, Kp/32
@@ -40,6 +42,7 @@ struct HPhase2Args {
   float* gt_part;       // [grid][Kp]
   double* cost_part;    // [grid]
   int probe;            // print the MMA issuer's wait/issue clocks of CTA 0 (diagnostics)
+  int nu;               // units of the streaming ring (even, 2..NU_MAX)
 };
 
 struct WPhase2Args {
@@ -50,11 +53,82 @@ struct WPhase2Args {
   long long T;
   const float* V;       // [T][ldv]
   float* Gpart;         // [ngroups][nchunk*128][Kp]
+  int nu;
 };
 
-__host__ __device__ constexpr size_t phase2_smem_bytes(int nkb) {
-  return (size_t)nkb * 16384 + (size_t)NSTA * KTILE_BYTES + (size_t)NSTB * nkb * SL * 128 + 2 * BM * 4 + 64 + 32 * 8 + 1024;
+__host__ __device__ constexpr size_t phase2_smem_bytes(int nkb, int nu) {
+  return (size_t)nkb * 16384 + (size_t)nu * UNIT + 2 * BM * 4 + 64 + 32 * 8 + 1024;
 }
+// largest even ring that fits beside the resident tile
+__host__ __device__ constexpr int phase2_units(int nkb, size_t max_smem) {
+  int nu = NU_MAX;
+  while (nu > 2 && phase2_smem_bytes(nkb, nu) > max_smem) nu -= 2;
+  return nu;
+}
+
+// Streaming ring, producer and consumer side.  Every unit goes through one full/empty cycle per round so that the
+// barrier parities follow from the position alone; a K-major tile takes two consecutive units (even position: an odd
+// position is padded with an empty cycle), its data completes on the first unit's barrier.
+struct RingProducer {
+  uint8_t* base; uint64_t* full; uint64_t* empty; uint32_t nu, p;
+  __device__ __forceinline__ uint32_t acquire(uint32_t pos) {
+    const uint32_t idx = pos % nu;
+    umma::mbar_wait(empty + idx, ((pos / nu) & 1) ^ 1);
+    return idx;
+  }
+  __device__ __forceinline__ void load_tile(const CUtensorMap* map, int x, int y) {
+    if (p & 1) {
+      const uint32_t idx = acquire(p);
+      umma::mbar_arrive(full + idx);
+      ++p;
+    }
+    const uint32_t i0 = acquire(p), i1 = acquire(p + 1);
+    umma::mbar_expect_tx(full + i0, KTILE_BYTES);
+    umma::tma_load_2d(base + (size_t)i0 * UNIT, map, full + i0, x, y);
+    umma::mbar_arrive(full + i1);
+    p += 2;
+  }
+  __device__ __forceinline__ void load_slice(const CUtensorMap* map, int nkb, int y) {
+    const uint32_t idx = acquire(p);
+    umma::mbar_expect_tx(full + idx, nkb * SL * 128);
+    for (int kb = 0; kb < nkb; ++kb) umma::tma_load_2d(base + (size_t)idx * UNIT + kb * SL * 128, map, full + idx, kb * KB, y);
+    ++p;
+  }
+};
+struct RingConsumer {
+  uint32_t base_addr; uint64_t* full; uint64_t* empty; uint32_t nu, p;
+  __device__ __forceinline__ uint32_t wait_full(uint32_t pos) {
+    const uint32_t idx = pos % nu;
+    umma::mbar_wait(full + idx, (pos / nu) & 1);
+    return idx;
+  }
+  // returns the shared-memory address of the tile; release_tile() after the MMAs that read it were issued
+  __device__ __forceinline__ uint32_t wait_tile() {
+    if (p & 1) {
+      const uint32_t idx = wait_full(p);
+      umma::mbar_arrive(empty + idx);
+      ++p;
+    }
+    const uint32_t i0 = wait_full(p);
+    wait_full(p + 1);
+    umma::tc_fence_after();
+    return base_addr + i0 * UNIT;
+  }
+  __device__ __forceinline__ void release_tile() {
+    umma::mma_commit(empty + (p % nu));
+    umma::mma_commit(empty + ((p + 1) % nu));
+    p += 2;
+  }
+  __device__ __forceinline__ uint32_t wait_slice() {
+    const uint32_t idx = wait_full(p);
+    umma::tc_fence_after();
+    return base_addr + idx * UNIT;
+  }
+  __device__ __forceinline__ void release_slice() {
+    umma::mma_commit(empty + (p % nu));
+    ++p;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------ H phase
 __global__ void __launch_bounds__(THREADS, 1)
@@ -64,11 +138,10 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int nkb = a.nkb, Kp = a.Kp, nblk = a.nblk;
-  const int sliceb = nkb * SL * 128;                      // bytes of one MN-major slice (all column blocks)
-  uint8_t* Hs = smem;                                     // nkb x [128 x 128 B]                 SW128, A of product 1
-  uint8_t* Ak = Hs + nkb * 16384;                         // NSTA x [256 x 128 B]                SW128 (K-major)
-  uint8_t* Bm = Ak + NSTA * KTILE_BYTES;                  // NSTB x nkb x [16 x 128 B]           SW128_ATOM_32B
-  float* vtail_s = (float*)(Bm + NSTB * sliceb);          // [128]
+  const int nu = a.nu;
+  uint8_t* Hs = smem;                                     // nkb x [128 x 128 B]   SW128, A of product 1
+  uint8_t* Rg = Hs + nkb * 16384;                         // nu x 16 KB streaming ring
+  float* vtail_s = (float*)(Rg + (size_t)nu * UNIT);      // [128]
   float* dotp = vtail_s + BM;                             // [128]
   double* red = (double*)(dotp + BM);                     // [8]
   uint64_t* bars = (uint64_t*)(red + 8);
@@ -77,12 +150,10 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
   uint64_t* num_full = bars + 2;
   uint64_t* num_empty = bars + 3;
   uint64_t* lam_full = bars + 4;
-  uint64_t* r_full = bars + 5;
-  uint64_t* a_full = bars + 6;                   // [NSTA]
-  uint64_t* a_empty = bars + 6 + NSTA;           // [NSTA]
-  uint64_t* b_full = bars + 6 + 2 * NSTA;        // [NSTB]
-  uint64_t* b_empty = bars + 6 + 2 * NSTA + NSTB;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * NSTA + 2 * NSTB);
+  uint64_t* r_full = bars + 5;                   // [2]: columns 0..127 / 128..255 of the Lambda block
+  uint64_t* u_full = bars + 7;                   // [NU_MAX]
+  uint64_t* u_empty = bars + 7 + NU_MAX;         // [NU_MAX]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 7 + 2 * NU_MAX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -92,13 +163,10 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     mbar_init(num_empty, 2 * BM);
     mbar_init(lam_full, 1);
     mbar_init(r_full, 2 * BM);
-    for (int i = 0; i < NSTA; ++i) {
-      mbar_init(a_full + i, 1);
-      mbar_init(a_empty + i, 1);
-    }
-    for (int i = 0; i < NSTB; ++i) {
-      mbar_init(b_full + i, 1);
-      mbar_init(b_empty + i, 1);
+    mbar_init(r_full + 1, 2 * BM);
+    for (int i = 0; i < NU_MAX; ++i) {
+      mbar_init(u_full + i, 1);
+      mbar_init(u_empty + i, 1);
     }
     fence_barrier_init();
   }
@@ -116,49 +184,22 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
       tma_prefetch_desc(&mapH);
       tma_prefetch_desc(&mapWk);
       tma_prefetch_desc(&mapWm);
-      uint32_t ga = 0, gb = 0;
-      auto load_k = [&](int b, int ks) {
-        const uint32_t s = ga % NSTA;
-        mbar_wait(a_empty + s, ((ga / NSTA) & 1) ^ 1);
-        mbar_expect_tx(a_full + s, KTILE_BYTES);
-        tma_load_2d(Ak + s * KTILE_BYTES, &mapWk, a_full + s, ks * KB, b * NB);
-        ++ga;
-      };
-      auto load_s = [&](int b, int js) {
-        const uint32_t s = gb % NSTB;
-        mbar_wait(b_empty + s, ((gb / NSTB) & 1) ^ 1);
-        mbar_expect_tx(b_full + s, sliceb);
-        for (int kb = 0; kb < nkb; ++kb)
-          tma_load_2d(Bm + s * sliceb + kb * SL * 128, &mapWm, b_full + s, kb * KB, b * NB + js * SL);
-        ++gb;
-      };
-      // the first PRE K-major tiles of a block are requested while the previous block is still in its second product
-      // (the dictionary does not depend on the frame tile, so this also runs across tile boundaries)
-      const int PRE = nkb < NSTA ? nkb : NSTA;
-      for (int ks = 0; ks < PRE; ++ks) load_k(0, ks);
+      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u};
       int it = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
         const int t0 = tile * BM;
+        // the dictionary does not depend on the frame tile: the first K-major tiles of this tile's first block go out
+        // before the wait for the previous tile's write-back
+        const int early = nkb < (nu / 2) ? nkb : (nu / 2);
+        for (int ks = 0; ks < early; ++ks) ring.load_tile(&mapWk, ks * KB, 0);
         mbar_wait(h_empty, (it & 1) ^ 1);
         mbar_expect_tx(h_full, nkb * 16384);
         for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Hs + kb * 16384, &mapH, h_full, kb * KB, t0);
         for (int b = 0; b < nblk; ++b) {
-          for (int ks = PRE; ks < nkb; ++ks) load_k(b, ks);
+          for (int ks = (b == 0 ? early : 0); ks < nkb; ++ks) ring.load_tile(&mapWk, ks * KB, b * NB);
           const int Nb = (b == nblk - 1) ? a.nlast : NB;
           const int nsl = upd ? Nb / SL : 0;
-          const bool has_next = (b + 1 < nblk) || (it + 1 < my_tiles);
-          const int nb = (b + 1 < nblk) ? b + 1 : 0;
-          bool pre_done = false;
-          for (int js = 0; js < nsl; ++js) {
-            load_s(b, js);
-            if (!pre_done && (js == 1 || js == nsl - 1)) {
-              if (has_next)
-                for (int ks = 0; ks < PRE; ++ks) load_k(nb, ks);
-              pre_done = true;
-            }
-          }
-          if (!pre_done && has_next)
-            for (int ks = 0; ks < PRE; ++ks) load_k(nb, ks);
+          for (int js = 0; js < nsl; ++js) ring.load_slice(&mapWm, nkb, b * NB + js * SL);
         }
       }
     }
@@ -166,8 +207,9 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0 && my_tiles > 0) {
       const uint32_t id2 = idesc_tf32(BM, Kp, 0, 1);
-      const uint32_t hs_a = smem_u32(Hs), ak_a = smem_u32(Ak), bm_a = smem_u32(Bm);
-      uint32_t ga = 0, gb = 0, g = 0;
+      const uint32_t hs_a = smem_u32(Hs);
+      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
+      uint32_t g = 0;
       int it = 0;
       long long p_h = 0, p_a = 0, p_i1 = 0, p_r = 0, p_i2 = 0, p_t0 = clock64();
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
@@ -179,48 +221,51 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
           const int Nb = (b == nblk - 1) ? a.nlast : NB;
           const uint32_t id1 = idesc_tf32(BM, Nb, 0, 0);
           // Lambda block = H_tile * W_block'
-          for (int ks = 0; ks < nkb; ++ks, ++ga) {
-            const uint32_t s = ga % NSTA;
+          for (int ks = 0; ks < nkb; ++ks) {
             q0 = clock64();
-            mbar_wait(a_full + s, (ga / NSTA) & 1);
+            const uint32_t tb = ring.wait_tile();
             p_a += clock64() - q0;
             q0 = clock64();
-            tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t da = smem_desc(hs_a + ks * 16384 + kk * 32, 16, 1024);
-              const uint64_t db = smem_desc(ak_a + s * KTILE_BYTES + kk * 32, 16, 1024);
+              const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
               mma_ss(tmem + LAM_COL, da, db, id1, (ks > 0) || (kk > 0));
             }
-            mma_commit(a_empty + s);
+            ring.release_tile();
             p_i1 += clock64() - q0;
           }
           mma_commit(lam_full);
+          // Num += R block * W_block, the first 128 columns of R as soon as the epilogue has turned them over
           q0 = clock64();
           mbar_wait(r_full, g & 1);
           p_r += clock64() - q0;
           tc_fence_after();
-          if (upd) {
-            if (b == 0) {
-              mbar_wait(num_empty, (it & 1) ^ 1);
-              tc_fence_after();
-            }
-            // Num += R block * W_block
-            q0 = clock64();
-            for (int js = 0; js < Nb / SL; ++js, ++gb) {
-              const uint32_t s = gb % NSTB;
-              mbar_wait(b_full + s, (gb / NSTB) & 1);
-              tc_fence_after();
-#pragma unroll
-              for (int j = 0; j < SL / 8; ++j) {
-                const uint64_t db = smem_desc(bm_a + s * sliceb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
-                mma_ts(tmem, tmem + LAM_COL + SL * js + 8 * j, db, id2, (b > 0) || (js > 0) || (j > 0));
-              }
-              mma_commit(b_empty + s);
-            }
-            if (b == nblk - 1) mma_commit(num_full);
-            p_i2 += clock64() - q0;
+          if (upd && b == 0) {
+            mbar_wait(num_empty, (it & 1) ^ 1);
+            tc_fence_after();
           }
+          q0 = clock64();
+          const int nsl = upd ? Nb / SL : 0;
+          for (int js = 0; js < nsl; ++js) {
+            if (js == 128 / SL) {
+              mbar_wait(r_full + 1, g & 1);
+              tc_fence_after();
+            }
+            const uint32_t sb = ring.wait_slice();
+#pragma unroll
+            for (int j = 0; j < SL / 8; ++j) {
+              const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
+              mma_ts(tmem, tmem + LAM_COL + SL * js + 8 * j, db, id2, (b > 0) || (js > 0) || (j > 0));
+            }
+            ring.release_slice();
+          }
+          if (nsl <= 128 / SL) {   // keep in step with the second half's barrier even when it carried no columns
+            mbar_wait(r_full + 1, g & 1);
+            tc_fence_after();
+          }
+          if (upd && b == nblk - 1) mma_commit(num_full);
+          p_i2 += clock64() - q0;
         }
       }
       if (a.probe && blockIdx.x == 0)
@@ -250,36 +295,42 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
       };
       for (int b = 0; b < nblk; ++b, ++g) {
         const int Nb = (b == nblk - 1) ? a.nlast : NB;
-        const int c_lo = 128 * e;
+        // both groups work on columns 0..127 first (64 each), hand them to the second product, then on 128..255
+        auto chunk_c0 = [&](int idx) { return 128 * (idx >> 1) + 64 * e + 32 * (idx & 1); };
         float vn[32];
-        if (c_lo < Nb) load_v(b * NB + c_lo, vn);          // in flight while the first product runs
+        if (chunk_c0(0) < Nb) load_v(b * NB + chunk_c0(0), vn);          // in flight while the first product runs
         mbar_wait(lam_full, g & 1);
         tc_fence_after();
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c0 = c_lo + 32 * cc;
-          if (c0 >= Nb) break;
-          float v[32];
+#pragma unroll 1
+        for (int idx = 0; idx < 4; ++idx) {
+          const int c0 = chunk_c0(idx);
+          if (c0 < Nb) {
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = vn[j];
-          if (cc + 1 < 4 && c0 + 32 < Nb) load_v(b * NB + c0 + 32, vn);
-          uint32_t lam[32];
-          tmem_ld32(lane_addr + LAM_COL + c0, lam);
-          tmem_wait_ld();
-          const int f0 = b * NB + c0;
+            for (int j = 0; j < 32; ++j) v[j] = vn[j];
+            const int nx = idx + 1 < 4 ? chunk_c0(idx + 1) : Nb;
+            if (nx < Nb) load_v(b * NB + nx, vn);
+            uint32_t lam[32];
+            tmem_ld32(lane_addr + LAM_COL + c0, lam);
+            tmem_wait_ld();
+            const int f0 = b * NB + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool ok = row_ok && (f0 + j < a.Fm);
-            const float vv = fmaxf(v[j], FLRF);                     // sparse_nmf.m:169
-            const float ll = fmaxf(__uint_as_float(lam[j]), FLRF);  // :167,208
-            const float r = __fdividef(vv, ll);
-            lam[j] = ok ? to_tf32_rn(r) : 0u;
-            if (a.want_cost && ok) cost_tile += vv * __logf(r) - vv + ll;  // :250
+            for (int j = 0; j < 32; ++j) {
+              const bool ok = row_ok && (f0 + j < a.Fm);
+              const float vv = fmaxf(v[j], FLRF);                     // sparse_nmf.m:169
+              const float ll = fmaxf(__uint_as_float(lam[j]), FLRF);  // :167,208
+              const float r = __fdividef(vv, ll);
+              lam[j] = ok ? to_tf32_rn(r) : 0u;
+              if (a.want_cost && ok) cost_tile += vv * __logf(r) - vv + ll;  // :250
+            }
+            if (upd) tmem_st32(lane_addr + LAM_COL + c0, lam);
           }
-          if (upd) tmem_st32(lane_addr + LAM_COL + c0, lam);
+          if (idx & 1) {
+            if (upd) tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(r_full + (idx >> 1));
+          }
         }
-        if (upd) tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(r_full);
       }
       // ---- the bin that stays off the tensor cores: Lambda(tail, frame) = W(tail,:) * h (state before the update)
       mbar_wait(h_full, it & 1);
@@ -412,20 +463,17 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int nkb = a.nkb, Kp = a.Kp;
-  const int sliceb = nkb * SL * 128;
+  const int nu = a.nu;
   uint8_t* Wc = smem;                                  // nkb x [128 x 128 B]   resident dictionary rows
-  uint8_t* Ak = Wc + nkb * 16384;                      // NSTA x [256 x 128 B]  K-major tiles of H'
-  uint8_t* Bm = Ak + NSTA * KTILE_BYTES;               // NSTB x nkb x [16 x 128 B]  MN-major slices of H'
-  uint64_t* bars = (uint64_t*)(Bm + NSTB * sliceb);
+  uint8_t* Rg = Wc + nkb * 16384;                      // nu x 16 KB streaming ring (tiles / slices of H')
+  uint64_t* bars = (uint64_t*)(Rg + (size_t)nu * UNIT);
   uint64_t* wc_full = bars + 0;
   uint64_t* g_full = bars + 1;
   uint64_t* lam_full = bars + 2;
-  uint64_t* r_full = bars + 3;
-  uint64_t* a_full = bars + 4;
-  uint64_t* a_empty = bars + 4 + NSTA;
-  uint64_t* b_full = bars + 4 + 2 * NSTA;
-  uint64_t* b_empty = bars + 4 + 2 * NSTA + NSTB;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 4 + 2 * NSTA + 2 * NSTB);
+  uint64_t* r_full = bars + 3;                   // [2]
+  uint64_t* u_full = bars + 5;
+  uint64_t* u_empty = bars + 5 + NU_MAX;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 5 + 2 * NU_MAX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -433,13 +481,10 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     mbar_init(g_full, 1);
     mbar_init(lam_full, 1);
     mbar_init(r_full, 2 * BM);
-    for (int i = 0; i < NSTA; ++i) {
-      mbar_init(a_full + i, 1);
-      mbar_init(a_empty + i, 1);
-    }
-    for (int i = 0; i < NSTB; ++i) {
-      mbar_init(b_full + i, 1);
-      mbar_init(b_empty + i, 1);
+    mbar_init(r_full + 1, 2 * BM);
+    for (int i = 0; i < NU_MAX; ++i) {
+      mbar_init(u_full + i, 1);
+      mbar_init(u_empty + i, 1);
     }
     fence_barrier_init();
   }
@@ -464,76 +509,56 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       tma_prefetch_desc(&mapHm);
       mbar_expect_tx(wc_full, nkb * 16384);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Wc + kb * 16384, &mapW, wc_full, kb * KB, chunk * BM);
-      uint32_t ga = 0, gb = 0;
-      auto load_k = [&](int i, int ks) {
-        const uint32_t s = ga % NSTA;
-        mbar_wait(a_empty + s, ((ga / NSTA) & 1) ^ 1);
-        mbar_expect_tx(a_full + s, KTILE_BYTES);
-        tma_load_2d(Ak + s * KTILE_BYTES, &mapHk, a_full + s, ks * KB, (grp + i * a.ngroups) * NB);
-        ++ga;
-      };
-      auto load_s = [&](int i, int js) {
-        const uint32_t s = gb % NSTB;
-        mbar_wait(b_empty + s, ((gb / NSTB) & 1) ^ 1);
-        mbar_expect_tx(b_full + s, sliceb);
-        for (int kb = 0; kb < nkb; ++kb)
-          tma_load_2d(Bm + s * sliceb + kb * SL * 128, &mapHm, b_full + s, kb * KB, (grp + i * a.ngroups) * NB + js * SL);
-        ++gb;
-      };
-      const int PRE = nkb < NSTA ? nkb : NSTA;
-      for (int ks = 0; ks < PRE; ++ks) load_k(0, ks);
+      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u};
       for (int i = 0; i < n_my; ++i) {
-        for (int ks = PRE; ks < nkb; ++ks) load_k(i, ks);
+        const int y = (grp + i * a.ngroups) * NB;
+        for (int ks = 0; ks < nkb; ++ks) ring.load_tile(&mapHk, ks * KB, y);
         const int nsl = block_n(i) / SL;
-        const bool has_next = i + 1 < n_my;
-        bool pre_done = false;
-        for (int js = 0; js < nsl; ++js) {
-          load_s(i, js);
-          if (!pre_done && (js == 1 || js == nsl - 1)) {
-            if (has_next)
-              for (int ks = 0; ks < PRE; ++ks) load_k(i + 1, ks);
-            pre_done = true;
-          }
-        }
+        for (int js = 0; js < nsl; ++js) ring.load_slice(&mapHm, nkb, y + js * SL);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_my > 0) {
       const uint32_t id4 = idesc_tf32(BM, Kp, 0, 1);
-      const uint32_t wc_a = smem_u32(Wc), ak_a = smem_u32(Ak), bm_a = smem_u32(Bm);
+      const uint32_t wc_a = smem_u32(Wc);
+      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
       mbar_wait(wc_full, 0);
       tc_fence_after();
-      uint32_t ga = 0, gb = 0;
       for (int i = 0; i < n_my; ++i) {
         const int Nb = block_n(i);
         const uint32_t id3 = idesc_tf32(BM, Nb, 0, 0);
         // Lambda block = W_rows * H'_block'
-        for (int ks = 0; ks < nkb; ++ks, ++ga) {
-          const uint32_t s = ga % NSTA;
-          mbar_wait(a_full + s, (ga / NSTA) & 1);
-          tc_fence_after();
+        for (int ks = 0; ks < nkb; ++ks) {
+          const uint32_t tb = ring.wait_tile();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t da = smem_desc(wc_a + ks * 16384 + kk * 32, 16, 1024);
-            const uint64_t db = smem_desc(ak_a + s * KTILE_BYTES + kk * 32, 16, 1024);
+            const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
             mma_ss(tmem + LAM_COL, da, db, id3, (ks > 0) || (kk > 0));
           }
-          mma_commit(a_empty + s);
+          ring.release_tile();
         }
         mma_commit(lam_full);
         mbar_wait(r_full, i & 1);
         tc_fence_after();
         // G += R block * H'_block
-        for (int js = 0; js < Nb / SL; ++js, ++gb) {
-          const uint32_t s = gb % NSTB;
-          mbar_wait(b_full + s, (gb / NSTB) & 1);
-          tc_fence_after();
+        const int nsl = Nb / SL;
+        for (int js = 0; js < nsl; ++js) {
+          if (js == 128 / SL) {
+            mbar_wait(r_full + 1, i & 1);
+            tc_fence_after();
+          }
+          const uint32_t sb = ring.wait_slice();
 #pragma unroll
           for (int j = 0; j < SL / 8; ++j) {
-            const uint64_t db = smem_desc(bm_a + s * sliceb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
+            const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
             mma_ts(tmem, tmem + LAM_COL + SL * js + 8 * j, db, id4, (i > 0) || (js > 0) || (j > 0));
           }
-          mma_commit(b_empty + s);
+          ring.release_slice();
+        }
+        if (nsl <= 128 / SL) {
+          mbar_wait(r_full + 1, i & 1);
+          tc_fence_after();
         }
         if (i == n_my - 1) mma_commit(g_full);
       }
@@ -547,37 +572,42 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     for (int i = 0; i < n_my; ++i) {
       const int Nb = block_n(i);
       const long long tb = (long long)(grp + i * a.ngroups) * NB;
-      const int c_lo = 128 * e;
+      auto chunk_c0 = [&](int idx) { return 128 * (idx >> 1) + 64 * e + 32 * (idx & 1); };
       auto load_v = [&](int c0, float (&dst)[32]) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           dst[j] = (f_ok && tb + c0 + j < a.T) ? __ldg(a.V + (size_t)(tb + c0 + j) * a.ldv + f) : 0.f;
       };
       float vn[32];
-      if (c_lo < Nb) load_v(c_lo, vn);
+      if (chunk_c0(0) < Nb) load_v(chunk_c0(0), vn);
       mbar_wait(lam_full, i & 1);
       tc_fence_after();
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = c_lo + 32 * cc;
-        if (c0 >= Nb) break;
-        float v[32];
+#pragma unroll 1
+      for (int idx = 0; idx < 4; ++idx) {
+        const int c0 = chunk_c0(idx);
+        if (c0 < Nb) {
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = vn[j];
-        if (cc + 1 < 4 && c0 + 32 < Nb) load_v(c0 + 32, vn);
-        uint32_t lam[32];
-        tmem_ld32(lane_addr + LAM_COL + c0, lam);
-        tmem_wait_ld();
+          for (int j = 0; j < 32; ++j) v[j] = vn[j];
+          const int nx = idx + 1 < 4 ? chunk_c0(idx + 1) : Nb;
+          if (nx < Nb) load_v(nx, vn);
+          uint32_t lam[32];
+          tmem_ld32(lane_addr + LAM_COL + c0, lam);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = f_ok && (tb + c0 + j < a.T);
-          const float r = __fdividef(fmaxf(v[j], FLRF), fmaxf(__uint_as_float(lam[j]), FLRF));
-          lam[j] = ok ? to_tf32_rn(r) : 0u;
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = f_ok && (tb + c0 + j < a.T);
+            const float r = __fdividef(fmaxf(v[j], FLRF), fmaxf(__uint_as_float(lam[j]), FLRF));
+            lam[j] = ok ? to_tf32_rn(r) : 0u;
+          }
+          tmem_st32(lane_addr + LAM_COL + c0, lam);
         }
-        tmem_st32(lane_addr + LAM_COL + c0, lam);
+        if (idx & 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(r_full + (idx >> 1));
+        }
       }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(r_full);
     }
     // ---- G tile -> this group's partial in HBM
     float* gout = a.Gpart + ((size_t)grp * a.nchunk * BM + (size_t)chunk * BM + row) * Kp;
