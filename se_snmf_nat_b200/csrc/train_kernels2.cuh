@@ -289,10 +289,19 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
       const bool row_ok = (t0 + row) < a.T;
       const float* vcol = a.Vt + t0 + row;
       float cost_tile = 0.f;
+      // the epilogue is issue-bound (two warps per scheduler): whole in-range chunks take a path without per-element
+      // predicates or address arithmetic
       auto load_v = [&](int f0, float (&dst)[32]) {
+        if (row_ok && f0 + 32 <= a.Fm) {
+          const float* pv = vcol + (size_t)f0 * a.ldt;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = (row_ok && f0 + j < a.Fm) ? __ldg(vcol + (size_t)(f0 + j) * a.ldt) : 0.f;
+          for (int j = 0; j < 32; ++j) dst[j] = __ldg(pv + (size_t)j * a.ldt);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[j] = (row_ok && f0 + j < a.Fm) ? __ldg(vcol + (size_t)(f0 + j) * a.ldt) : 0.f;
+        }
       };
+      float cost_lg = 0.f, cost_lin = 0.f;   // sum v*log2(v/lambda), sum (lambda - v)
       for (int b = 0; b < nblk; ++b, ++g) {
         const int Nb = (b == nblk - 1) ? a.nlast : NB;
         // both groups work on columns 0..127 first (64 each), hand them to the second product, then on 128..255
@@ -314,14 +323,35 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
             tmem_ld32(lane_addr + LAM_COL + c0, lam);
             tmem_wait_ld();
             const int f0 = b * NB + c0;
+            if (row_ok && f0 + 32 <= a.Fm) {
+              if (a.want_cost) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool ok = row_ok && (f0 + j < a.Fm);
-              const float vv = fmaxf(v[j], FLRF);                     // sparse_nmf.m:169
-              const float ll = fmaxf(__uint_as_float(lam[j]), FLRF);  // :167,208
-              const float r = __fdividef(vv, ll);
-              lam[j] = ok ? to_tf32_rn(r) : 0u;
-              if (a.want_cost && ok) cost_tile += vv * __logf(r) - vv + ll;  // :250
+                for (int j = 0; j < 32; ++j) {
+                  const float vv = fmaxf(v[j], FLRF);                     // sparse_nmf.m:169
+                  const float ll = fmaxf(__uint_as_float(lam[j]), FLRF);  // :167,208
+                  const float r = __fdividef(vv, ll);
+                  lam[j] = to_tf32_rn(r);
+                  cost_lg = fmaf(vv, __log2f(r), cost_lg);                // :250, v*log(v/lambda) = ln2 * v*log2(r)
+                  cost_lin += ll - vv;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float vv = fmaxf(v[j], FLRF);
+                  const float ll = fmaxf(__uint_as_float(lam[j]), FLRF);
+                  lam[j] = to_tf32_rn(__fdividef(vv, ll));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const bool ok = row_ok && (f0 + j < a.Fm);
+                const float vv = fmaxf(v[j], FLRF);
+                const float ll = fmaxf(__uint_as_float(lam[j]), FLRF);
+                const float r = __fdividef(vv, ll);
+                lam[j] = ok ? to_tf32_rn(r) : 0u;
+                if (a.want_cost && ok) cost_tile += vv * __logf(r) - vv + ll;
+              }
             }
             if (upd) tmem_st32(lane_addr + LAM_COL + c0, lam);
           }
@@ -356,7 +386,7 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
         if (e == 0) vtail_s[row] = vv;
         r_t = __uint_as_float(to_tf32_rn(r_t));
       }
-      cost_acc += (double)cost_tile;
+      cost_acc += (double)cost_tile + (double)(0.69314718f * cost_lg + cost_lin);
       if (upd) {
         // ---- H' = H .* Num ./ dph  (sparse_nmf.m:192-195), in place in the shared-memory tile
         mbar_wait(num_full, it & 1);
@@ -574,9 +604,15 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       const long long tb = (long long)(grp + i * a.ngroups) * NB;
       auto chunk_c0 = [&](int idx) { return 128 * (idx >> 1) + 64 * e + 32 * (idx & 1); };
       auto load_v = [&](int c0, float (&dst)[32]) {
+        if (f_ok && tb + c0 + 32 <= a.T) {
+          const float* pv = a.V + (size_t)(tb + c0) * a.ldv + f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          dst[j] = (f_ok && tb + c0 + j < a.T) ? __ldg(a.V + (size_t)(tb + c0 + j) * a.ldv + f) : 0.f;
+          for (int j = 0; j < 32; ++j) dst[j] = __ldg(pv + (size_t)j * a.ldv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            dst[j] = (f_ok && tb + c0 + j < a.T) ? __ldg(a.V + (size_t)(tb + c0 + j) * a.ldv + f) : 0.f;
+        }
       };
       float vn[32];
       if (chunk_c0(0) < Nb) load_v(chunk_c0(0), vn);
@@ -594,11 +630,17 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           uint32_t lam[32];
           tmem_ld32(lane_addr + LAM_COL + c0, lam);
           tmem_wait_ld();
+          if (f_ok && tb + c0 + 32 <= a.T) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool ok = f_ok && (tb + c0 + j < a.T);
-            const float r = __fdividef(fmaxf(v[j], FLRF), fmaxf(__uint_as_float(lam[j]), FLRF));
-            lam[j] = ok ? to_tf32_rn(r) : 0u;
+            for (int j = 0; j < 32; ++j)
+              lam[j] = to_tf32_rn(__fdividef(fmaxf(v[j], FLRF), fmaxf(__uint_as_float(lam[j]), FLRF)));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool ok = f_ok && (tb + c0 + j < a.T);
+              const float r = __fdividef(fmaxf(v[j], FLRF), fmaxf(__uint_as_float(lam[j]), FLRF));
+              lam[j] = ok ? to_tf32_rn(r) : 0u;
+            }
           }
           tmem_st32(lane_addr + LAM_COL + c0, lam);
         }
