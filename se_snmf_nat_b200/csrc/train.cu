@@ -80,6 +80,8 @@ struct snmfnat_train {
   CUtensorMap mHk256[2], mHm16[2], mWk256[2], mWm16[2];
   int v2 = 1;                 // SNMFNAT_TRAIN_V1=1 selects the first-generation kernels
   int nblk_h = 0, nlast_h = 0, nblocks_w = 0, nu = 2;
+  int csz_h = 1, csz_w = 1;   // cluster sizes that share a stream by TMA multicast (SNMFNAT_TRAIN_MC=0 disables)
+  CUtensorMap mHkP[2], mWkP[2];  // K-major part tiles: box of 256 / csz rows
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   double* h_scal = nullptr;  // pinned: [0] = div
@@ -285,8 +287,20 @@ void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
   a.probe = (update && t->iters_done == 0 && t->dbg_h.p) ? 1 : 0;
   a.nu = t->nu;
   const int ch = t->cur_h, cw = t->cur_w;
-  hphase2_kernel<<<t->grid_h, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1],
-                                                                                     t->mWk256[cw], t->mWm16[cw], a);
+  a.csz = t->csz_h;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(t->grid_h);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = phase2_smem_bytes(t->nkb, t->nu);
+    cfg.stream = t->ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = t->csz_h; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SN_CUDA(cudaLaunchKernelEx(&cfg, hphase2_kernel, t->mH128[ch], t->mH128[ch ^ 1],
+                               t->csz_h > 1 ? t->mWkP[cw] : t->mWk256[cw], t->mWm16[cw], a));
+  }
   count_launch(t->ctx);
   check_launch(t->ctx, "hphase2_kernel");
 }
@@ -298,8 +312,20 @@ void launch_wphase2(snmfnat_train* t, int hbuf) {
   a.V = t->V.p; a.Gpart = t->Gpart.p;
   a.nu = t->nu;
   const int grid = t->nchunk * t->ngroups, cw = t->cur_w;
-  wphase2_kernel<<<grid, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mW128[cw], t->mHk256[hbuf],
-                                                                                t->mHm16[hbuf], a);
+  a.csz = t->csz_w;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = phase2_smem_bytes(t->nkb, t->nu);
+    cfg.stream = t->ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = t->csz_w; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SN_CUDA(cudaLaunchKernelEx(&cfg, wphase2_kernel, t->mW128[cw], t->csz_w > 1 ? t->mHkP[hbuf] : t->mHk256[hbuf],
+                               t->mHm16[hbuf], a));
+  }
   count_launch(t->ctx);
   check_launch(t->ctx, "wphase2_kernel");
 }
@@ -454,6 +480,41 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
     t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nblocks_w));
     SN_CUDA(cudaFuncSetAttribute(hphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
     SN_CUDA(cudaFuncSetAttribute(wphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
+    // Clusters that share a stream by TMA multicast: pairs of frame tiles share the dictionary in the H phase, the bin
+    // chunks of one frame group share H' in the W phase.  The grids follow from how many such clusters the device
+    // keeps resident (GPC sizes), so that nothing queues behind a first wave.
+    // Measured on B200 (1.25M frames, K = 256): 4.83 ms per iteration with multicast against 4.66 ms without.  The
+    // streams are bound by what one SM can take in (~40 B/clk), which multicast to <= 4 CTAs does not change, so it is
+    // OFF unless SNMFNAT_TRAIN_MC=1 (kept parity-tested).
+    const char* mc = getenv("SNMFNAT_TRAIN_MC");
+    const bool want_mc = (mc && mc[0] == '1');
+    auto max_clusters = [&](const void* fn, int csz) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(csz * ctx->sm_count);
+      cfg.blockDim = dim3(THREADS);
+      cfg.dynamicSmemBytes = phase2_smem_bytes(t->nkb, t->nu);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      return n;
+    };
+    if (want_mc && t->nkb % 2 == 0 && t->ntiles >= 4) {
+      const int nc2 = max_clusters((const void*)hphase2_kernel, 2);
+      if (nc2 * 2 >= ctx->sm_count - 8) {   // keep (almost) every SM busy
+        t->csz_h = 2;
+        t->grid_h = std::min(2 * nc2, t->ntiles & ~1);
+      }
+    }
+    if (want_mc && (t->nchunk == 2 || t->nchunk == 4) && t->nkb % t->nchunk == 0) {
+      const int ncw = max_clusters((const void*)wphase2_kernel, t->nchunk);
+      if (ncw * t->nchunk >= ctx->sm_count - 16) {
+        t->csz_w = t->nchunk;
+        t->ngroups = std::max(1, std::min(ncw, t->nblocks_w));
+      }
+    }
   }
   SN_REQUIRE(hphase_smem(t.get()) <= (size_t)ctx->max_smem_optin && wphase_smem(t.get()) <= (size_t)ctx->max_smem_optin,
              SNMFNAT_EUNSUPPORTED, "shared memory: need %zu / %zu bytes, device offers %d", hphase_smem(t.get()),
@@ -511,6 +572,8 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
     make_map(&t->mHm16[i], t->H[i].p, t->Kp, T_local, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     make_map(&t->mWk256[i], t->Wt[i].p, t->Kp, F, pitch, NB);
     make_map(&t->mWm16[i], t->Wt[i].p, t->Kp, F, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    make_map(&t->mHkP[i], t->H[i].p, t->Kp, T_local, pitch, NB / t->csz_w);
+    make_map(&t->mWkP[i], t->Wt[i].p, t->Kp, F, pitch, NB / t->csz_h);
   }
   SN_CUDA(cudaStreamSynchronize(st));
   *out = t.release();

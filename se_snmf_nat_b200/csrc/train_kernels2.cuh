@@ -43,6 +43,7 @@ struct HPhase2Args {
   double* cost_part;    // [grid]
   int probe;            // print the MMA issuer's wait/issue clocks of CTA 0 (diagnostics)
   int nu;               // units of the streaming ring (even, 2..NU_MAX)
+  int csz;              // CTAs per cluster that share the dictionary stream by TMA multicast (1 = none)
 };
 
 struct WPhase2Args {
@@ -54,6 +55,7 @@ struct WPhase2Args {
   const float* V;       // [T][ldv]
   float* Gpart;         // [ngroups][nchunk*128][Kp]
   int nu;
+  int csz;              // = nchunk when the chunk CTAs of a frame group share the stream of H' by TMA multicast, else 1
 };
 
 __host__ __device__ constexpr size_t phase2_smem_bytes(int nkb, int nu) {
@@ -69,13 +71,17 @@ __host__ __device__ constexpr int phase2_units(int nkb, size_t max_smem) {
 // Streaming ring, producer and consumer side.  Every unit goes through one full/empty cycle per round so that the
 // barrier parities follow from the position alone; a K-major tile takes two consecutive units (even position: an odd
 // position is padded with an empty cycle), its data completes on the first unit's barrier.
+// With csz > 1 the CTAs of a cluster stream the SAME tiles in lock step: each CTA requests 1/csz of every unit and TMA
+// multicasts it into all of them, so a CTA has csz times the bytes in flight for the same shared memory; a unit is
+// free again when all csz consumers have released it (empty barriers count csz arrivals).
 struct RingProducer {
-  uint8_t* base; uint64_t* full; uint64_t* empty; uint32_t nu, p;
+  uint8_t* base; uint64_t* full; uint64_t* empty; uint32_t nu, p, csz, rank;
   __device__ __forceinline__ uint32_t acquire(uint32_t pos) {
     const uint32_t idx = pos % nu;
     umma::mbar_wait(empty + idx, ((pos / nu) & 1) ^ 1);
     return idx;
   }
+  // `map` has a box of 256 / csz rows
   __device__ __forceinline__ void load_tile(const CUtensorMap* map, int x, int y) {
     if (p & 1) {
       const uint32_t idx = acquire(p);
@@ -84,29 +90,49 @@ struct RingProducer {
     }
     const uint32_t i0 = acquire(p), i1 = acquire(p + 1);
     umma::mbar_expect_tx(full + i0, KTILE_BYTES);
-    umma::tma_load_2d(base + (size_t)i0 * UNIT, map, full + i0, x, y);
+    if (csz == 1) {
+      umma::tma_load_2d(base + (size_t)i0 * UNIT, map, full + i0, x, y);
+    } else {
+      const uint32_t rows = NB / csz;
+      umma::tma_load_2d_mc(base + (size_t)i0 * UNIT + (size_t)rank * rows * 128, map, full + i0, x, y + (int)(rank * rows),
+                           (uint16_t)((1u << csz) - 1));
+    }
     umma::mbar_arrive(full + i1);
     p += 2;
   }
   __device__ __forceinline__ void load_slice(const CUtensorMap* map, int nkb, int y) {
     const uint32_t idx = acquire(p);
     umma::mbar_expect_tx(full + idx, nkb * SL * 128);
-    for (int kb = 0; kb < nkb; ++kb) umma::tma_load_2d(base + (size_t)idx * UNIT + kb * SL * 128, map, full + idx, kb * KB, y);
+    if (csz == 1) {
+      for (int kb = 0; kb < nkb; ++kb)
+        umma::tma_load_2d(base + (size_t)idx * UNIT + kb * SL * 128, map, full + idx, kb * KB, y);
+    } else {
+      const int per = nkb / (int)csz;   // the host only picks csz > 1 when it divides nkb
+      for (int kb = (int)rank * per; kb < ((int)rank + 1) * per; ++kb)
+        umma::tma_load_2d_mc(base + (size_t)idx * UNIT + kb * SL * 128, map, full + idx, kb * KB, y,
+                             (uint16_t)((1u << csz) - 1));
+    }
     ++p;
   }
 };
 struct RingConsumer {
-  uint32_t base_addr; uint64_t* full; uint64_t* empty; uint32_t nu, p;
+  uint32_t base_addr; uint64_t* full; uint64_t* empty; uint32_t nu, p, csz;
   __device__ __forceinline__ uint32_t wait_full(uint32_t pos) {
     const uint32_t idx = pos % nu;
     umma::mbar_wait(full + idx, (pos / nu) & 1);
     return idx;
   }
+  __device__ __forceinline__ void release(uint32_t idx) {   // when the MMAs issued so far have completed
+    if (csz == 1) umma::mma_commit(empty + idx);
+    else umma::mma_commit_mc(empty + idx, (uint16_t)((1u << csz) - 1));
+  }
   // returns the shared-memory address of the tile; release_tile() after the MMAs that read it were issued
   __device__ __forceinline__ uint32_t wait_tile() {
     if (p & 1) {
       const uint32_t idx = wait_full(p);
-      umma::mbar_arrive(empty + idx);
+      if (csz == 1) umma::mbar_arrive(empty + idx);
+      else
+        for (uint32_t c = 0; c < csz; ++c) umma::mbar_arrive_remote(empty + idx, c);
       ++p;
     }
     const uint32_t i0 = wait_full(p);
@@ -115,8 +141,8 @@ struct RingConsumer {
     return base_addr + i0 * UNIT;
   }
   __device__ __forceinline__ void release_tile() {
-    umma::mma_commit(empty + (p % nu));
-    umma::mma_commit(empty + ((p + 1) % nu));
+    release(p % nu);
+    release((p + 1) % nu);
     p += 2;
   }
   __device__ __forceinline__ uint32_t wait_slice() {
@@ -125,7 +151,7 @@ struct RingConsumer {
     return base_addr + idx * UNIT;
   }
   __device__ __forceinline__ void release_slice() {
-    umma::mma_commit(empty + (p % nu));
+    release(p % nu);
     ++p;
   }
 };
@@ -166,7 +192,7 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     mbar_init(r_full + 1, 2 * BM);
     for (int i = 0; i < NU_MAX; ++i) {
       mbar_init(u_full + i, 1);
-      mbar_init(u_empty + i, 1);
+      mbar_init(u_empty + i, a.csz);
     }
     fence_barrier_init();
   }
@@ -174,9 +200,15 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const uint32_t csz = (uint32_t)a.csz;
+  const uint32_t crank = csz > 1 ? cluster_ctarank() : 0u;
+  if (csz > 1) cluster_sync_all();   // every CTA's barriers exist before a peer multicasts into / arrives on them
   const uint32_t tmem = *tmem_slot;
   const bool upd = a.update != 0;
-  const int my_tiles = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // every CTA runs the same number of tiles (the CTAs of a cluster consume the shared stream in lock step); a tile
+  // index >= ntiles is an all-padding tile: loads read zeros, nothing is stored, nothing is accumulated
+  const int my_tiles = (a.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_end = my_tiles * (int)gridDim.x;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -184,9 +216,9 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
       tma_prefetch_desc(&mapH);
       tma_prefetch_desc(&mapWk);
       tma_prefetch_desc(&mapWm);
-      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u};
+      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u, csz, crank};
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         const int t0 = tile * BM;
         // the dictionary does not depend on the frame tile: the first K-major tiles of this tile's first block go out
         // before the wait for the previous tile's write-back
@@ -208,11 +240,11 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     if (lane == 0 && my_tiles > 0) {
       const uint32_t id2 = idesc_tf32(BM, Kp, 0, 1);
       const uint32_t hs_a = smem_u32(Hs);
-      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
+      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u, csz};
       uint32_t g = 0;
       int it = 0;
       long long p_h = 0, p_a = 0, p_i1 = 0, p_r = 0, p_i2 = 0, p_t0 = clock64();
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         long long q0 = clock64();
         mbar_wait(h_full, it & 1);
         p_h += clock64() - q0;
@@ -269,9 +301,9 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
         }
       }
       if (a.probe && blockIdx.x == 0)
-        printf("hphase2 probe (MMA issuer, CTA 0): total %lld clk, %d tiles x %d blocks | wait h_full %lld, wait K tiles %lld, "
-               "issue MMA1 %lld, wait r_full %lld, MMA2 (issue + slice waits) %lld\n",
-               clock64() - p_t0, it, nblk, p_h, p_a, p_i1, p_r, p_i2);
+        printf("hphase2 probe (MMA issuer, CTA 0; ring %d units, cluster %d, grid %d): total %lld clk, %d tiles x %d blocks | "
+               "wait h_full %lld, wait K tiles %lld, issue MMA1 %lld, wait r_full %lld, MMA2 (issue + slice waits) %lld\n",
+               nu, (int)csz, (int)gridDim.x, clock64() - p_t0, it, nblk, p_h, p_a, p_i1, p_r, p_i2);
     }
   } else {
     // ===================================================================== epilogue: two groups of 128 threads
@@ -284,7 +316,7 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     double cost_acc = 0.0;
     uint32_t g = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const long long t0 = (long long)tile * BM;
       const bool row_ok = (t0 + row) < a.T;
       const float* vcol = a.Vt + t0 + row;
@@ -483,6 +515,7 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
+  if (csz > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it or arrive on its barriers
 }
 
 // ------------------------------------------------------------------------------------------------ W phase
@@ -514,7 +547,7 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     mbar_init(r_full + 1, 2 * BM);
     for (int i = 0; i < NU_MAX; ++i) {
       mbar_init(u_full + i, 1);
-      mbar_init(u_empty + i, 1);
+      mbar_init(u_empty + i, a.csz);
     }
     fence_barrier_init();
   }
@@ -522,6 +555,9 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const uint32_t csz = (uint32_t)a.csz;
+  const uint32_t crank = csz > 1 ? cluster_ctarank() : 0u;
+  if (csz > 1) cluster_sync_all();
   const uint32_t tmem = *tmem_slot;
   const int chunk = blockIdx.x % a.nchunk, grp = blockIdx.x / a.nchunk;
   const int n_my = (a.nblocks > grp) ? (a.nblocks - grp + a.ngroups - 1) / a.ngroups : 0;
@@ -539,7 +575,7 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       tma_prefetch_desc(&mapHm);
       mbar_expect_tx(wc_full, nkb * 16384);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Wc + kb * 16384, &mapW, wc_full, kb * KB, chunk * BM);
-      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u};
+      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u, csz, crank};
       for (int i = 0; i < n_my; ++i) {
         const int y = (grp + i * a.ngroups) * NB;
         for (int ks = 0; ks < nkb; ++ks) ring.load_tile(&mapHk, ks * KB, y);
@@ -551,7 +587,7 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     if (lane == 0 && n_my > 0) {
       const uint32_t id4 = idesc_tf32(BM, Kp, 0, 1);
       const uint32_t wc_a = smem_u32(Wc);
-      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
+      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u, csz};
       mbar_wait(wc_full, 0);
       tc_fence_after();
       for (int i = 0; i < n_my; ++i) {
@@ -677,6 +713,7 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
+  if (csz > 1) cluster_sync_all();
 }
 
 }  // namespace train
