@@ -76,12 +76,10 @@ struct snmfnat_train {
   DevBuf<float> dbg_h, dbg_w;  // diagnostics (SNMFNAT_TRAIN_DEBUG=1)
   int cur_h = 0, cur_w = 0;
   CUtensorMap mH128[2], mHk[2], mHm[2], mWk[2], mWm[2], mW128[2];
-  // second-generation kernels (train_kernels2.cuh): 256-row K-major tiles and 16-row MN-major slices
-  CUtensorMap mHk256[2], mHm16[2], mWk256[2], mWm16[2];
+  // second-generation kernels (train_kernels2.cuh): 128-row K-major tiles (mH128 / mW128) and 16-row MN-major slices
+  CUtensorMap mHm16[2], mWm16[2];
   int v2 = 1;                 // SNMFNAT_TRAIN_V1=1 selects the first-generation kernels
   int nblk_h = 0, nlast_h = 0, nblocks_w = 0, nu = 2;
-  int csz_h = 1, csz_w = 1;   // cluster sizes that share a stream by TMA multicast (SNMFNAT_TRAIN_MC=0 disables)
-  CUtensorMap mHkP[2], mWkP[2];  // K-major part tiles: box of 256 / csz rows
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   double* h_scal = nullptr;  // pinned: [0] = div
@@ -123,6 +121,21 @@ void make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SN_REQUIRE(r == CUDA_SUCCESS, SNMFNAT_ECUDA, "cuTensorMapEncodeTiled failed with %d (inner %llu outer %llu pitch %llu)",
              (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch);
+}
+
+// 3-D view of a [outer][Kp] fp32 matrix as {32 floats, outer rows, Kp/32 column blocks}, box {32, box_rows, nkb}: one
+// TMA instruction delivers box_rows rows of EVERY column block, stacked column block by column block.
+void make_map_slices(CUtensorMap* m, const float* base, int nkb, uint64_t outer, uint64_t pitch, uint32_t box_rows,
+                     CUtensorMapSwizzle swz) {
+  cuuint64_t dims[3] = {(cuuint64_t)KB, outer, (cuuint64_t)nkb};
+  cuuint64_t strides[2] = {pitch, (cuuint64_t)KB * 4};
+  cuuint32_t box[3] = {(cuuint32_t)KB, box_rows, (cuuint32_t)nkb};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SN_REQUIRE(r == CUDA_SUCCESS, SNMFNAT_ECUDA, "cuTensorMapEncodeTiled (3-D slices) failed with %d (outer %llu pitch %llu nkb %d)",
+             (int)r, (unsigned long long)outer, (unsigned long long)pitch, nkb);
 }
 
 __device__ __forceinline__ double blk_sum256(double v, double* sh) {
@@ -277,7 +290,7 @@ size_t wphase_smem(const snmfnat_train* t) {
 void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
   HPhase2Args a;
   a.F = t->F; a.Fm = t->tail_row >= 0 ? t->F - 1 : t->F; a.Kp = t->Kp; a.nkb = t->nkb;
-  a.nblk = t->nblk_h; a.nlast = t->nlast_h;
+  a.nh = t->nblk_h; a.nlast = t->nlast_h;
   a.ntiles = t->ntiles;
   a.update = update; a.want_cost = want_cost; a.tail_row = t->tail_row;
   a.T = t->T; a.ldt = t->ldt;
@@ -287,20 +300,8 @@ void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
   a.probe = (update && t->iters_done == 0 && t->dbg_h.p) ? 1 : 0;
   a.nu = t->nu;
   const int ch = t->cur_h, cw = t->cur_w;
-  a.csz = t->csz_h;
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(t->grid_h);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = phase2_smem_bytes(t->nkb, t->nu);
-    cfg.stream = t->ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = t->csz_h; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    SN_CUDA(cudaLaunchKernelEx(&cfg, hphase2_kernel, t->mH128[ch], t->mH128[ch ^ 1],
-                               t->csz_h > 1 ? t->mWkP[cw] : t->mWk256[cw], t->mWm16[cw], a));
-  }
+  hphase2_kernel<<<t->grid_h, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1],
+                                                                                            t->mW128[cw], t->mWm16[cw], a);
   count_launch(t->ctx);
   check_launch(t->ctx, "hphase2_kernel");
 }
@@ -312,20 +313,8 @@ void launch_wphase2(snmfnat_train* t, int hbuf) {
   a.V = t->V.p; a.Gpart = t->Gpart.p;
   a.nu = t->nu;
   const int grid = t->nchunk * t->ngroups, cw = t->cur_w;
-  a.csz = t->csz_w;
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = phase2_smem_bytes(t->nkb, t->nu);
-    cfg.stream = t->ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = t->csz_w; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    SN_CUDA(cudaLaunchKernelEx(&cfg, wphase2_kernel, t->mW128[cw], t->csz_w > 1 ? t->mHkP[hbuf] : t->mHk256[hbuf],
-                               t->mHm16[hbuf], a));
-  }
+  wphase2_kernel<<<grid, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mW128[cw], t->mH128[hbuf],
+                                                                                       t->mHm16[hbuf], a);
   count_launch(t->ctx);
   check_launch(t->ctx, "wphase2_kernel");
 }
@@ -474,47 +463,12 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
   t->v2 = (getenv("SNMFNAT_TRAIN_V1") == nullptr && phase2_smem_bytes(t->nkb, t->nu) <= (size_t)ctx->max_smem_optin) ? 1 : 0;
   if (t->v2) {
     const int Fm = t->tail_row >= 0 ? F - 1 : F;
-    t->nblk_h = (Fm + NB - 1) / NB;
-    t->nlast_h = (Fm - (t->nblk_h - 1) * NB + 15) / 16 * 16;
-    t->nblocks_w = (int)((T_local + NB - 1) / NB);
+    t->nblk_h = (Fm + HB - 1) / HB;
+    t->nlast_h = (Fm - (t->nblk_h - 1) * HB + 15) / 16 * 16;
+    t->nblocks_w = (int)((T_local + HB - 1) / HB);
     t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nblocks_w));
     SN_CUDA(cudaFuncSetAttribute(hphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
     SN_CUDA(cudaFuncSetAttribute(wphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
-    // Clusters that share a stream by TMA multicast: pairs of frame tiles share the dictionary in the H phase, the bin
-    // chunks of one frame group share H' in the W phase.  The grids follow from how many such clusters the device
-    // keeps resident (GPC sizes), so that nothing queues behind a first wave.
-    // Measured on B200 (1.25M frames, K = 256): 4.83 ms per iteration with multicast against 4.66 ms without.  The
-    // streams are bound by what one SM can take in (~40 B/clk), which multicast to <= 4 CTAs does not change, so it is
-    // OFF unless SNMFNAT_TRAIN_MC=1 (kept parity-tested).
-    const char* mc = getenv("SNMFNAT_TRAIN_MC");
-    const bool want_mc = (mc && mc[0] == '1');
-    auto max_clusters = [&](const void* fn, int csz) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(csz * ctx->sm_count);
-      cfg.blockDim = dim3(THREADS);
-      cfg.dynamicSmemBytes = phase2_smem_bytes(t->nkb, t->nu);
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-      return n;
-    };
-    if (want_mc && t->nkb % 2 == 0 && t->ntiles >= 4) {
-      const int nc2 = max_clusters((const void*)hphase2_kernel, 2);
-      if (nc2 * 2 >= ctx->sm_count - 8) {   // keep (almost) every SM busy
-        t->csz_h = 2;
-        t->grid_h = std::min(2 * nc2, t->ntiles & ~1);
-      }
-    }
-    if (want_mc && (t->nchunk == 2 || t->nchunk == 4) && t->nkb % t->nchunk == 0) {
-      const int ncw = max_clusters((const void*)wphase2_kernel, t->nchunk);
-      if (ncw * t->nchunk >= ctx->sm_count - 16) {
-        t->csz_w = t->nchunk;
-        t->ngroups = std::max(1, std::min(ncw, t->nblocks_w));
-      }
-    }
   }
   SN_REQUIRE(hphase_smem(t.get()) <= (size_t)ctx->max_smem_optin && wphase_smem(t.get()) <= (size_t)ctx->max_smem_optin,
              SNMFNAT_EUNSUPPORTED, "shared memory: need %zu / %zu bytes, device offers %d", hphase_smem(t.get()),
@@ -568,12 +522,8 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
     make_map(&t->mWk[i], t->Wt[i].p, t->Kp, F, pitch, t->nc);
     make_map(&t->mWm[i], t->Wt[i].p, t->Kp, F, pitch, t->nc, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     make_map(&t->mW128[i], t->Wt[i].p, t->Kp, F, pitch, BM);
-    make_map(&t->mHk256[i], t->H[i].p, t->Kp, T_local, pitch, NB);
-    make_map(&t->mHm16[i], t->H[i].p, t->Kp, T_local, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    make_map(&t->mWk256[i], t->Wt[i].p, t->Kp, F, pitch, NB);
-    make_map(&t->mWm16[i], t->Wt[i].p, t->Kp, F, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    make_map(&t->mHkP[i], t->H[i].p, t->Kp, T_local, pitch, NB / t->csz_w);
-    make_map(&t->mWkP[i], t->Wt[i].p, t->Kp, F, pitch, NB / t->csz_h);
+    make_map_slices(&t->mHm16[i], t->H[i].p, t->nkb, T_local, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    make_map_slices(&t->mWm16[i], t->Wt[i].p, t->nkb, F, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   }
   SN_CUDA(cudaStreamSynchronize(st));
   *out = t.release();

@@ -4,13 +4,14 @@
 // of M = 128 reads its A operand at one 128-byte row per clock, i.e. ~128 clk per instruction whatever N is, while the
 // tensor pipe itself needs N/2 clk.  The first-generation kernels streamed the other matrix in 16-row chunks, so the
 // first product (Lambda = A * chunk') ran with N = 16: 97 clk per instruction measured, 6-9 % of the tensor pipe.
-// Here the first product is issued with N = 256:
-//   * Lambda block [128 x 256] = A_tile [128 x Kp] * X_block' with X_block = 256 rows of the streamed matrix, delivered
-//     as K-major tiles [256 rows x 32 atoms] (32 KB): every instruction is M128 x N256 x K8, A-read time == tensor time.
-//   * the epilogue warps turn the whole 256-column Lambda block into R = V ./ Lambda in place in tensor memory
-//     (V prefetched from HBM while the MMAs run),
-//   * the second product Acc += R * X_block reads R from tensor memory and X_block as MN-major 16-row slices (as before).
-// Tensor memory: accumulator (Kp <= 256 columns) + one Lambda block (256 columns) = 512 columns.
+// Here:
+//   * the first product is issued with N = 128: Lambda buffer [128 x 128] = A_tile [128 x Kp] * X_half' with X_half =
+//     128 rows of the streamed matrix, delivered as K-major tiles [128 rows x 32 atoms] (16 KB),
+//   * there are TWO Lambda buffers in tensor memory (2 x 128 columns beside the <= 256 accumulator columns), so the
+//     first product of half c+1 runs while the epilogue warps turn half c into R = V ./ Lambda in place (V is
+//     prefetched from HBM one 32-column chunk ahead) and the second product Acc += R * X_half of half c-1 follows,
+//   * one ring of 16 KB units feeds both products in consumption order (a K-major tile or an MN-major 16-row slice per
+//     unit), so all the shared memory beside the resident tile is in flight for whichever product is running.
 // In the H phase the Nyquist bin (F % 128 == 1) stays off the tensor cores: its Lambda is a dot product per frame in
 // the epilogue and its contribution to the numerator a rank-1 term of the H update.
 #pragma once
@@ -19,18 +20,14 @@
 namespace snmfnat {
 namespace train {
 
-constexpr int NB = 256;        // columns of one Lambda block (N of the first product)
+constexpr int HB = 128;        // columns of one Lambda buffer (N of the first product)
 constexpr int SL = 16;         // rows of one MN-major slice of the second product
-constexpr int KTILE_BYTES = NB * 128;
-// One ring of 16 KB units feeds both products in consumption order (K-major tile = 2 units, MN-major slice = 1 unit),
-// so whatever shared memory is left beside the resident tile is in flight for the product that is running: the
-// loads are latency-bound (bytes in flight / L2 latency), not bandwidth-bound.
-constexpr int UNIT = 16384;
+constexpr int UNIT = 16384;    // ring unit: one K-major tile [128 x 128 B] or one slice [nkb][16 x 128 B]
 constexpr int NU_MAX = 8;
 
 struct HPhase2Args {
   int F, Fm, Kp, nkb;  // bins, bins that go through the tensor cores, padded rank, Kp/32
-  int nblk, nlast;     // 256-bin blocks, N of the last block (multiple of 16)
+  int nh, nlast;       // 128-bin halves, N of the last one (multiple of 16)
   int ntiles;
   int update, want_cost;
   int tail_row;        // F-1 when that bin is handled by the epilogue (F % 128 == 1), else -1
@@ -42,116 +39,63 @@ struct HPhase2Args {
   float* gt_part;       // [grid][Kp]
   double* cost_part;    // [grid]
   int probe;            // print the MMA issuer's wait/issue clocks of CTA 0 (diagnostics)
-  int nu;               // units of the streaming ring (even, 2..NU_MAX)
-  int csz;              // CTAs per cluster that share the dictionary stream by TMA multicast (1 = none)
+  int nu;               // units of the streaming ring (2..NU_MAX)
 };
 
 struct WPhase2Args {
   int F, Kp, nkb;
   int nchunk, ngroups;  // 128-bin chunks; frame groups (grid = nchunk * ngroups)
-  int nblocks;          // ceil(T / 256)
+  int nblocks;          // ceil(T / 128)
   int ldv;
   long long T;
   const float* V;       // [T][ldv]
   float* Gpart;         // [ngroups][nchunk*128][Kp]
   int nu;
-  int csz;              // = nchunk when the chunk CTAs of a frame group share the stream of H' by TMA multicast, else 1
 };
 
 __host__ __device__ constexpr size_t phase2_smem_bytes(int nkb, int nu) {
   return (size_t)nkb * 16384 + (size_t)nu * UNIT + 2 * BM * 4 + 64 + 32 * 8 + 1024;
 }
-// largest even ring that fits beside the resident tile
+// largest ring that fits beside the resident tile
 __host__ __device__ constexpr int phase2_units(int nkb, size_t max_smem) {
   int nu = NU_MAX;
-  while (nu > 2 && phase2_smem_bytes(nkb, nu) > max_smem) nu -= 2;
+  while (nu > 2 && phase2_smem_bytes(nkb, nu) > max_smem) --nu;
   return nu;
 }
 
-// Streaming ring, producer and consumer side.  Every unit goes through one full/empty cycle per round so that the
-// barrier parities follow from the position alone; a K-major tile takes two consecutive units (even position: an odd
-// position is padded with an empty cycle), its data completes on the first unit's barrier.
-// With csz > 1 the CTAs of a cluster stream the SAME tiles in lock step: each CTA requests 1/csz of every unit and TMA
-// multicasts it into all of them, so a CTA has csz times the bytes in flight for the same shared memory; a unit is
-// free again when all csz consumers have released it (empty barriers count csz arrivals).
+// Streaming ring, producer and consumer side: unit `pos % nu`, barrier parities follow from the position.
 struct RingProducer {
-  uint8_t* base; uint64_t* full; uint64_t* empty; uint32_t nu, p, csz, rank;
-  __device__ __forceinline__ uint32_t acquire(uint32_t pos) {
-    const uint32_t idx = pos % nu;
-    umma::mbar_wait(empty + idx, ((pos / nu) & 1) ^ 1);
+  uint8_t* base; uint64_t* full; uint64_t* empty; uint32_t nu, p;
+  __device__ __forceinline__ uint32_t acquire() {
+    const uint32_t idx = p % nu;
+    umma::mbar_wait(empty + idx, ((p / nu) & 1) ^ 1);
     return idx;
   }
-  // `map` has a box of 256 / csz rows
-  __device__ __forceinline__ void load_tile(const CUtensorMap* map, int x, int y) {
-    if (p & 1) {
-      const uint32_t idx = acquire(p);
-      umma::mbar_arrive(full + idx);
-      ++p;
-    }
-    const uint32_t i0 = acquire(p), i1 = acquire(p + 1);
-    umma::mbar_expect_tx(full + i0, KTILE_BYTES);
-    if (csz == 1) {
-      umma::tma_load_2d(base + (size_t)i0 * UNIT, map, full + i0, x, y);
-    } else {
-      const uint32_t rows = NB / csz;
-      umma::tma_load_2d_mc(base + (size_t)i0 * UNIT + (size_t)rank * rows * 128, map, full + i0, x, y + (int)(rank * rows),
-                           (uint16_t)((1u << csz) - 1));
-    }
-    umma::mbar_arrive(full + i1);
-    p += 2;
+  __device__ __forceinline__ void load_tile(const CUtensorMap* map, int x, int y) {   // box {32, 128}
+    const uint32_t idx = acquire();
+    umma::mbar_expect_tx(full + idx, UNIT);
+    umma::tma_load_2d(base + (size_t)idx * UNIT, map, full + idx, x, y);
+    ++p;
   }
+  // one 3-D box {32 floats, 16 rows, nkb column blocks}: the slice arrives as nkb consecutive [16 x 128 B] blocks with
+  // ONE TMA instruction (eight 2 KB boxes per slice made the second product TMA-issue-bound: ~100 clk per box)
   __device__ __forceinline__ void load_slice(const CUtensorMap* map, int nkb, int y) {
-    const uint32_t idx = acquire(p);
+    const uint32_t idx = acquire();
     umma::mbar_expect_tx(full + idx, nkb * SL * 128);
-    if (csz == 1) {
-      for (int kb = 0; kb < nkb; ++kb)
-        umma::tma_load_2d(base + (size_t)idx * UNIT + kb * SL * 128, map, full + idx, kb * KB, y);
-    } else {
-      const int per = nkb / (int)csz;   // the host only picks csz > 1 when it divides nkb
-      for (int kb = (int)rank * per; kb < ((int)rank + 1) * per; ++kb)
-        umma::tma_load_2d_mc(base + (size_t)idx * UNIT + kb * SL * 128, map, full + idx, kb * KB, y,
-                             (uint16_t)((1u << csz) - 1));
-    }
+    umma::tma_load_3d(base + (size_t)idx * UNIT, map, full + idx, 0, y, 0);
     ++p;
   }
 };
 struct RingConsumer {
-  uint32_t base_addr; uint64_t* full; uint64_t* empty; uint32_t nu, p, csz;
-  __device__ __forceinline__ uint32_t wait_full(uint32_t pos) {
-    const uint32_t idx = pos % nu;
-    umma::mbar_wait(full + idx, (pos / nu) & 1);
-    return idx;
-  }
-  __device__ __forceinline__ void release(uint32_t idx) {   // when the MMAs issued so far have completed
-    if (csz == 1) umma::mma_commit(empty + idx);
-    else umma::mma_commit_mc(empty + idx, (uint16_t)((1u << csz) - 1));
-  }
-  // returns the shared-memory address of the tile; release_tile() after the MMAs that read it were issued
-  __device__ __forceinline__ uint32_t wait_tile() {
-    if (p & 1) {
-      const uint32_t idx = wait_full(p);
-      if (csz == 1) umma::mbar_arrive(empty + idx);
-      else
-        for (uint32_t c = 0; c < csz; ++c) umma::mbar_arrive_remote(empty + idx, c);
-      ++p;
-    }
-    const uint32_t i0 = wait_full(p);
-    wait_full(p + 1);
-    umma::tc_fence_after();
-    return base_addr + i0 * UNIT;
-  }
-  __device__ __forceinline__ void release_tile() {
-    release(p % nu);
-    release((p + 1) % nu);
-    p += 2;
-  }
-  __device__ __forceinline__ uint32_t wait_slice() {
-    const uint32_t idx = wait_full(p);
+  uint32_t base_addr; uint64_t* full; uint64_t* empty; uint32_t nu, p;
+  __device__ __forceinline__ uint32_t wait() {   // shared-memory address of the next unit
+    const uint32_t idx = p % nu;
+    umma::mbar_wait(full + idx, (p / nu) & 1);
     umma::tc_fence_after();
     return base_addr + idx * UNIT;
   }
-  __device__ __forceinline__ void release_slice() {
-    release(p % nu);
+  __device__ __forceinline__ void release() {    // free again when the MMAs issued so far have completed
+    umma::mma_commit(empty + (p % nu));
     ++p;
   }
 };
@@ -163,7 +107,7 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
   using namespace umma;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  const int nkb = a.nkb, Kp = a.Kp, nblk = a.nblk;
+  const int nkb = a.nkb, Kp = a.Kp, nh = a.nh;
   const int nu = a.nu;
   uint8_t* Hs = smem;                                     // nkb x [128 x 128 B]   SW128, A of product 1
   uint8_t* Rg = Hs + nkb * 16384;                         // nu x 16 KB streaming ring
@@ -175,11 +119,11 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
   uint64_t* h_empty = bars + 1;
   uint64_t* num_full = bars + 2;
   uint64_t* num_empty = bars + 3;
-  uint64_t* lam_full = bars + 4;
-  uint64_t* r_full = bars + 5;                   // [2]: columns 0..127 / 128..255 of the Lambda block
-  uint64_t* u_full = bars + 7;                   // [NU_MAX]
-  uint64_t* u_empty = bars + 7 + NU_MAX;         // [NU_MAX]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 7 + 2 * NU_MAX);
+  uint64_t* lam_full = bars + 4;                 // [2]
+  uint64_t* r_full = bars + 6;                   // [2]
+  uint64_t* u_full = bars + 8;                   // [NU_MAX]
+  uint64_t* u_empty = bars + 8 + NU_MAX;         // [NU_MAX]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8 + 2 * NU_MAX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -187,12 +131,13 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     mbar_init(h_empty, 1);
     mbar_init(num_full, 1);
     mbar_init(num_empty, 2 * BM);
-    mbar_init(lam_full, 1);
-    mbar_init(r_full, 2 * BM);
-    mbar_init(r_full + 1, 2 * BM);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(lam_full + i, 1);
+      mbar_init(r_full + i, 2 * BM);
+    }
     for (int i = 0; i < NU_MAX; ++i) {
       mbar_init(u_full + i, 1);
-      mbar_init(u_empty + i, a.csz);
+      mbar_init(u_empty + i, 1);
     }
     fence_barrier_init();
   }
@@ -200,123 +145,118 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t csz = (uint32_t)a.csz;
-  const uint32_t crank = csz > 1 ? cluster_ctarank() : 0u;
-  if (csz > 1) cluster_sync_all();   // every CTA's barriers exist before a peer multicasts into / arrives on them
   const uint32_t tmem = *tmem_slot;
   const bool upd = a.update != 0;
-  // every CTA runs the same number of tiles (the CTAs of a cluster consume the shared stream in lock step); a tile
-  // index >= ntiles is an all-padding tile: loads read zeros, nothing is stored, nothing is accumulated
-  const int my_tiles = (a.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tile_end = my_tiles * (int)gridDim.x;
+  auto half_n = [&](int c) { return c == nh - 1 ? a.nlast : HB; };
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0 && my_tiles > 0) {
+    if (lane == 0 && (int)blockIdx.x < a.ntiles) {
       tma_prefetch_desc(&mapH);
       tma_prefetch_desc(&mapWk);
       tma_prefetch_desc(&mapWm);
-      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u, csz, crank};
+      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u};
       int it = 0;
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
         const int t0 = tile * BM;
-        // the dictionary does not depend on the frame tile: the first K-major tiles of this tile's first block go out
-        // before the wait for the previous tile's write-back
+        // the dictionary does not depend on the frame tile: the first K-major tiles of this tile go out before the
+        // wait for the previous tile's write-back
         const int early = nkb < (nu / 2) ? nkb : (nu / 2);
         for (int ks = 0; ks < early; ++ks) ring.load_tile(&mapWk, ks * KB, 0);
         mbar_wait(h_empty, (it & 1) ^ 1);
         mbar_expect_tx(h_full, nkb * 16384);
         for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Hs + kb * 16384, &mapH, h_full, kb * KB, t0);
-        for (int b = 0; b < nblk; ++b) {
-          for (int ks = (b == 0 ? early : 0); ks < nkb; ++ks) ring.load_tile(&mapWk, ks * KB, b * NB);
-          const int Nb = (b == nblk - 1) ? a.nlast : NB;
-          const int nsl = upd ? Nb / SL : 0;
-          for (int js = 0; js < nsl; ++js) ring.load_slice(&mapWm, nkb, b * NB + js * SL);
+        for (int c = 0; c <= nh; ++c) {   // same order as the MMA issuer consumes
+          if (c < nh)
+            for (int ks = (c == 0 ? early : 0); ks < nkb; ++ks) ring.load_tile(&mapWk, ks * KB, c * HB);
+          if (c >= 1 && upd)
+            for (int js = 0; js < half_n(c - 1) / SL; ++js) ring.load_slice(&mapWm, nkb, (c - 1) * HB + js * SL);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one thread)
-    if (lane == 0 && my_tiles > 0) {
+    if (lane == 0 && (int)blockIdx.x < a.ntiles) {
       const uint32_t id2 = idesc_tf32(BM, Kp, 0, 1);
       const uint32_t hs_a = smem_u32(Hs);
-      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u, csz};
-      uint32_t g = 0;
+      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
+      uint32_t n = 0;
       int it = 0;
-      long long p_h = 0, p_a = 0, p_i1 = 0, p_r = 0, p_i2 = 0, p_t0 = clock64();
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+      long long p_h = 0, p_a = 0, p_i1 = 0, p_r = 0, p_i2 = 0, p_sw = 0, p_t0 = clock64();
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
         long long q0 = clock64();
         mbar_wait(h_full, it & 1);
         p_h += clock64() - q0;
         tc_fence_after();
-        for (int b = 0; b < nblk; ++b, ++g) {
-          const int Nb = (b == nblk - 1) ? a.nlast : NB;
-          const uint32_t id1 = idesc_tf32(BM, Nb, 0, 0);
-          // Lambda block = H_tile * W_block'
-          for (int ks = 0; ks < nkb; ++ks) {
-            q0 = clock64();
-            const uint32_t tb = ring.wait_tile();
-            p_a += clock64() - q0;
-            q0 = clock64();
+        const uint32_t nbase = n;
+        for (int c = 0; c <= nh; ++c) {
+          if (c < nh) {  // Lambda(c) = H_tile * W_half(c)'
+            const uint32_t m = nbase + c, b = m & 1;
+            const uint32_t id1 = idesc_tf32(BM, half_n(c), 0, 0);
+            for (int ks = 0; ks < nkb; ++ks) {
+              q0 = clock64();
+              const uint32_t tb = ring.wait();
+              p_a += clock64() - q0;
+              q0 = clock64();
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = smem_desc(hs_a + ks * 16384 + kk * 32, 16, 1024);
-              const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
-              mma_ss(tmem + LAM_COL, da, db, id1, (ks > 0) || (kk > 0));
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t da = smem_desc(hs_a + ks * 16384 + kk * 32, 16, 1024);
+                const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
+                mma_ss(tmem + LAM_COL + HB * b, da, db, id1, (ks > 0) || (kk > 0));
+              }
+              ring.release();
+              p_i1 += clock64() - q0;
             }
-            ring.release_tile();
-            p_i1 += clock64() - q0;
+            mma_commit(lam_full + b);
           }
-          mma_commit(lam_full);
-          // Num += R block * W_block, the first 128 columns of R as soon as the epilogue has turned them over
-          q0 = clock64();
-          mbar_wait(r_full, g & 1);
-          p_r += clock64() - q0;
-          tc_fence_after();
-          if (upd && b == 0) {
-            mbar_wait(num_empty, (it & 1) ^ 1);
+          if (c >= 1) {  // Num += R(c-1) * W_half(c-1)
+            const uint32_t m = nbase + c - 1, b = m & 1;
+            q0 = clock64();
+            mbar_wait(r_full + b, (m >> 1) & 1);
+            p_r += clock64() - q0;
             tc_fence_after();
-          }
-          q0 = clock64();
-          const int nsl = upd ? Nb / SL : 0;
-          for (int js = 0; js < nsl; ++js) {
-            if (js == 128 / SL) {
-              mbar_wait(r_full + 1, g & 1);
-              tc_fence_after();
-            }
-            const uint32_t sb = ring.wait_slice();
+            if (upd) {
+              if (c == 1) {
+                mbar_wait(num_empty, (it & 1) ^ 1);
+                tc_fence_after();
+              }
+              q0 = clock64();
+              for (int js = 0; js < half_n(c - 1) / SL; ++js) {
+                const long long q1 = clock64();
+                const uint32_t sb = ring.wait();
+                p_sw += clock64() - q1;
 #pragma unroll
-            for (int j = 0; j < SL / 8; ++j) {
-              const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
-              mma_ts(tmem, tmem + LAM_COL + SL * js + 8 * j, db, id2, (b > 0) || (js > 0) || (j > 0));
+                for (int j = 0; j < SL / 8; ++j) {
+                  const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
+                  mma_ts(tmem, tmem + LAM_COL + HB * b + SL * js + 8 * j, db, id2, (c > 1) || (js > 0) || (j > 0));
+                }
+                ring.release();
+              }
+              if (c == nh) mma_commit(num_full);
+              p_i2 += clock64() - q0;
             }
-            ring.release_slice();
           }
-          if (nsl <= 128 / SL) {   // keep in step with the second half's barrier even when it carried no columns
-            mbar_wait(r_full + 1, g & 1);
-            tc_fence_after();
-          }
-          if (upd && b == nblk - 1) mma_commit(num_full);
-          p_i2 += clock64() - q0;
         }
+        n = nbase + nh;
       }
       if (a.probe && blockIdx.x == 0)
-        printf("hphase2 probe (MMA issuer, CTA 0; ring %d units, cluster %d, grid %d): total %lld clk, %d tiles x %d blocks | "
-               "wait h_full %lld, wait K tiles %lld, issue MMA1 %lld, wait r_full %lld, MMA2 (issue + slice waits) %lld\n",
-               nu, (int)csz, (int)gridDim.x, clock64() - p_t0, it, nblk, p_h, p_a, p_i1, p_r, p_i2);
+        printf("hphase2 probe (MMA issuer, CTA 0; ring %d units, grid %d): total %lld clk, %d tiles x %d halves | "
+               "wait h_full %lld, wait K tiles %lld, issue MMA1 %lld, wait r_full %lld, MMA2 (issue + slice waits) %lld of which slice "
+               "waits %lld\n",
+               nu, (int)gridDim.x, clock64() - p_t0, it, nh, p_h, p_a, p_i1, p_r, p_i2, p_sw);
     }
   } else {
     // ===================================================================== epilogue: two groups of 128 threads
-    const int e = (warp - 2) >> 2;           // group: columns [128 e, 128 e + 128) of a Lambda block
+    const int e = (warp - 2) >> 2;           // group: columns [64 e, 64 e + 64) of every Lambda buffer
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = 32 * q + lane;           // frame inside the tile
     const int etid = (warp - 2) * 32 + lane; // 0..255
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
     float hs_acc = 0.f, gt_acc = 0.f;
     double cost_acc = 0.0;
-    uint32_t g = 0;
+    uint32_t n = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const long long t0 = (long long)tile * BM;
       const bool row_ok = (t0 + row) < a.T;
       const float* vcol = a.Vt + t0 + row;
@@ -334,27 +274,29 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
         }
       };
       float cost_lg = 0.f, cost_lin = 0.f;   // sum v*log2(v/lambda), sum (lambda - v)
-      for (int b = 0; b < nblk; ++b, ++g) {
-        const int Nb = (b == nblk - 1) ? a.nlast : NB;
-        // both groups work on columns 0..127 first (64 each), hand them to the second product, then on 128..255
-        auto chunk_c0 = [&](int idx) { return 128 * (idx >> 1) + 64 * e + 32 * (idx & 1); };
-        float vn[32];
-        if (chunk_c0(0) < Nb) load_v(b * NB + chunk_c0(0), vn);          // in flight while the first product runs
-        mbar_wait(lam_full, g & 1);
+      // this thread's chunks of the tile, in order: (half c, 32-column chunk cc) -> first bin 128 c + 64 e + 32 cc
+      float vn[32];
+      load_v(64 * e, vn);                    // in flight while the first product of the tile runs
+      for (int c = 0; c < nh; ++c, ++n) {
+        const int Nh = half_n(c);
+        const uint32_t b = n & 1;
+        mbar_wait(lam_full + b, (n >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int idx = 0; idx < 4; ++idx) {
-          const int c0 = chunk_c0(idx);
-          if (c0 < Nb) {
-            float v[32];
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = 64 * e + 32 * cc;   // column inside the buffer
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = vn[j];
-            const int nx = idx + 1 < 4 ? chunk_c0(idx + 1) : Nb;
-            if (nx < Nb) load_v(b * NB + nx, vn);
+          for (int j = 0; j < 32; ++j) v[j] = vn[j];
+          {
+            const int nf = cc == 0 ? HB * c + c0 + 32 : HB * (c + 1) + 64 * e;   // first bin of the next chunk
+            if (nf < a.Fm) load_v(nf, vn);
+          }
+          if (c0 < Nh) {
             uint32_t lam[32];
-            tmem_ld32(lane_addr + LAM_COL + c0, lam);
+            tmem_ld32(lane_addr + LAM_COL + HB * b + c0, lam);
             tmem_wait_ld();
-            const int f0 = b * NB + c0;
+            const int f0 = HB * c + c0;
             if (row_ok && f0 + 32 <= a.Fm) {
               if (a.want_cost) {
 #pragma unroll
@@ -385,14 +327,12 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
                 if (a.want_cost && ok) cost_tile += vv * __logf(r) - vv + ll;
               }
             }
-            if (upd) tmem_st32(lane_addr + LAM_COL + c0, lam);
-          }
-          if (idx & 1) {
-            if (upd) tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(r_full + (idx >> 1));
+            if (upd) tmem_st32(lane_addr + LAM_COL + HB * b + c0, lam);
           }
         }
+        if (upd) tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(r_full + b);
       }
       // ---- the bin that stays off the tensor cores: Lambda(tail, frame) = W(tail,:) * h (state before the update)
       mbar_wait(h_full, it & 1);
@@ -515,7 +455,6 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
-  if (csz > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it or arrive on its barriers
 }
 
 // ------------------------------------------------------------------------------------------------ W phase
@@ -532,22 +471,23 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   uint64_t* bars = (uint64_t*)(Rg + (size_t)nu * UNIT);
   uint64_t* wc_full = bars + 0;
   uint64_t* g_full = bars + 1;
-  uint64_t* lam_full = bars + 2;
-  uint64_t* r_full = bars + 3;                   // [2]
-  uint64_t* u_full = bars + 5;
-  uint64_t* u_empty = bars + 5 + NU_MAX;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 5 + 2 * NU_MAX);
+  uint64_t* lam_full = bars + 2;                 // [2]
+  uint64_t* r_full = bars + 4;                   // [2]
+  uint64_t* u_full = bars + 6;
+  uint64_t* u_empty = bars + 6 + NU_MAX;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * NU_MAX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(wc_full, 1);
     mbar_init(g_full, 1);
-    mbar_init(lam_full, 1);
-    mbar_init(r_full, 2 * BM);
-    mbar_init(r_full + 1, 2 * BM);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(lam_full + i, 1);
+      mbar_init(r_full + i, 2 * BM);
+    }
     for (int i = 0; i < NU_MAX; ++i) {
       mbar_init(u_full + i, 1);
-      mbar_init(u_empty + i, a.csz);
+      mbar_init(u_empty + i, 1);
     }
     fence_barrier_init();
   }
@@ -555,17 +495,14 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t csz = (uint32_t)a.csz;
-  const uint32_t crank = csz > 1 ? cluster_ctarank() : 0u;
-  if (csz > 1) cluster_sync_all();
   const uint32_t tmem = *tmem_slot;
   const int chunk = blockIdx.x % a.nchunk, grp = blockIdx.x / a.nchunk;
   const int n_my = (a.nblocks > grp) ? (a.nblocks - grp + a.ngroups - 1) / a.ngroups : 0;
   // N of block i of this CTA (frames beyond T read as zero rows; N stays a multiple of 16)
   auto block_n = [&](int i) {
-    const long long t0 = (long long)(grp + i * a.ngroups) * NB;
+    const long long t0 = (long long)(grp + i * a.ngroups) * HB;
     const long long left = a.T - t0;
-    return left >= NB ? NB : (int)((left + 15) / 16 * 16);
+    return left >= HB ? HB : (int)((left + 15) / 16 * 16);
   };
 
   if (warp == 0) {
@@ -575,58 +512,54 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       tma_prefetch_desc(&mapHm);
       mbar_expect_tx(wc_full, nkb * 16384);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Wc + kb * 16384, &mapW, wc_full, kb * KB, chunk * BM);
-      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u, csz, crank};
-      for (int i = 0; i < n_my; ++i) {
-        const int y = (grp + i * a.ngroups) * NB;
-        for (int ks = 0; ks < nkb; ++ks) ring.load_tile(&mapHk, ks * KB, y);
-        const int nsl = block_n(i) / SL;
-        for (int js = 0; js < nsl; ++js) ring.load_slice(&mapHm, nkb, y + js * SL);
+      RingProducer ring{Rg, u_full, u_empty, (uint32_t)nu, 0u};
+      for (int i = 0; i <= n_my; ++i) {   // same order as the MMA issuer consumes
+        if (i < n_my)
+          for (int ks = 0; ks < nkb; ++ks) ring.load_tile(&mapHk, ks * KB, (grp + i * a.ngroups) * HB);
+        if (i >= 1)
+          for (int js = 0; js < block_n(i - 1) / SL; ++js)
+            ring.load_slice(&mapHm, nkb, (grp + (i - 1) * a.ngroups) * HB + js * SL);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_my > 0) {
       const uint32_t id4 = idesc_tf32(BM, Kp, 0, 1);
       const uint32_t wc_a = smem_u32(Wc);
-      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u, csz};
+      RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
       mbar_wait(wc_full, 0);
       tc_fence_after();
-      for (int i = 0; i < n_my; ++i) {
-        const int Nb = block_n(i);
-        const uint32_t id3 = idesc_tf32(BM, Nb, 0, 0);
-        // Lambda block = W_rows * H'_block'
-        for (int ks = 0; ks < nkb; ++ks) {
-          const uint32_t tb = ring.wait_tile();
+      for (int i = 0; i <= n_my; ++i) {
+        if (i < n_my) {  // Lambda(i) = W_rows * H'_block(i)'
+          const uint32_t b = i & 1;
+          const uint32_t id3 = idesc_tf32(BM, block_n(i), 0, 0);
+          for (int ks = 0; ks < nkb; ++ks) {
+            const uint32_t tb = ring.wait();
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t da = smem_desc(wc_a + ks * 16384 + kk * 32, 16, 1024);
-            const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
-            mma_ss(tmem + LAM_COL, da, db, id3, (ks > 0) || (kk > 0));
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = smem_desc(wc_a + ks * 16384 + kk * 32, 16, 1024);
+              const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
+              mma_ss(tmem + LAM_COL + HB * b, da, db, id3, (ks > 0) || (kk > 0));
+            }
+            ring.release();
           }
-          ring.release_tile();
+          mma_commit(lam_full + b);
         }
-        mma_commit(lam_full);
-        mbar_wait(r_full, i & 1);
-        tc_fence_after();
-        // G += R block * H'_block
-        const int nsl = Nb / SL;
-        for (int js = 0; js < nsl; ++js) {
-          if (js == 128 / SL) {
-            mbar_wait(r_full + 1, i & 1);
-            tc_fence_after();
-          }
-          const uint32_t sb = ring.wait_slice();
-#pragma unroll
-          for (int j = 0; j < SL / 8; ++j) {
-            const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
-            mma_ts(tmem, tmem + LAM_COL + SL * js + 8 * j, db, id4, (i > 0) || (js > 0) || (j > 0));
-          }
-          ring.release_slice();
-        }
-        if (nsl <= 128 / SL) {
-          mbar_wait(r_full + 1, i & 1);
+        if (i >= 1) {  // G += R(i-1) * H'_block(i-1)
+          const int m = i - 1;
+          const uint32_t b = m & 1;
+          mbar_wait(r_full + b, (m >> 1) & 1);
           tc_fence_after();
+          for (int js = 0; js < block_n(m) / SL; ++js) {
+            const uint32_t sb = ring.wait();
+#pragma unroll
+            for (int j = 0; j < SL / 8; ++j) {
+              const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
+              mma_ts(tmem, tmem + LAM_COL + HB * b + SL * js + 8 * j, db, id4, (m > 0) || (js > 0) || (j > 0));
+            }
+            ring.release();
+          }
+          if (m == n_my - 1) mma_commit(g_full);
         }
-        if (i == n_my - 1) mma_commit(g_full);
       }
     }
   } else {
@@ -635,36 +568,38 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     const int f = chunk * BM + row;
     const bool f_ok = f < a.F;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    // this thread's 32-frame chunks, in order: (block i, chunk cc) -> first frame (grp + i ngroups) 128 + 64 e + 32 cc
+    auto load_v = [&](long long tf, float (&dst)[32]) {
+      if (f_ok && tf + 32 <= a.T) {
+        const float* pv = a.V + (size_t)tf * a.ldv + f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = __ldg(pv + (size_t)j * a.ldv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = (f_ok && tf + j < a.T) ? __ldg(a.V + (size_t)(tf + j) * a.ldv + f) : 0.f;
+      }
+    };
+    float vn[32];
+    if (n_my > 0) load_v((long long)grp * HB + 64 * e, vn);
     for (int i = 0; i < n_my; ++i) {
       const int Nb = block_n(i);
-      const long long tb = (long long)(grp + i * a.ngroups) * NB;
-      auto chunk_c0 = [&](int idx) { return 128 * (idx >> 1) + 64 * e + 32 * (idx & 1); };
-      auto load_v = [&](int c0, float (&dst)[32]) {
-        if (f_ok && tb + c0 + 32 <= a.T) {
-          const float* pv = a.V + (size_t)(tb + c0) * a.ldv + f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dst[j] = __ldg(pv + (size_t)j * a.ldv);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            dst[j] = (f_ok && tb + c0 + j < a.T) ? __ldg(a.V + (size_t)(tb + c0 + j) * a.ldv + f) : 0.f;
-        }
-      };
-      float vn[32];
-      if (chunk_c0(0) < Nb) load_v(chunk_c0(0), vn);
-      mbar_wait(lam_full, i & 1);
+      const long long tb = (long long)(grp + i * a.ngroups) * HB;
+      const uint32_t b = i & 1;
+      mbar_wait(lam_full + b, (i >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int idx = 0; idx < 4; ++idx) {
-        const int c0 = chunk_c0(idx);
-        if (c0 < Nb) {
-          float v[32];
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = 64 * e + 32 * cc;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = vn[j];
-          const int nx = idx + 1 < 4 ? chunk_c0(idx + 1) : Nb;
-          if (nx < Nb) load_v(nx, vn);
+        for (int j = 0; j < 32; ++j) v[j] = vn[j];
+        {
+          const long long nf = cc == 0 ? tb + c0 + 32 : (long long)(grp + (i + 1) * a.ngroups) * HB + 64 * e;
+          if ((cc == 0 || i + 1 < n_my) && nf < a.T) load_v(nf, vn);
+        }
+        if (c0 < Nb) {
           uint32_t lam[32];
-          tmem_ld32(lane_addr + LAM_COL + c0, lam);
+          tmem_ld32(lane_addr + LAM_COL + HB * b + c0, lam);
           tmem_wait_ld();
           if (f_ok && tb + c0 + 32 <= a.T) {
 #pragma unroll
@@ -678,14 +613,12 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
               lam[j] = ok ? to_tf32_rn(r) : 0u;
             }
           }
-          tmem_st32(lane_addr + LAM_COL + c0, lam);
-        }
-        if (idx & 1) {
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(r_full + (idx >> 1));
+          tmem_st32(lane_addr + LAM_COL + HB * b + c0, lam);
         }
       }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(r_full + b);
     }
     // ---- G tile -> this group's partial in HBM
     float* gout = a.Gpart + ((size_t)grp * a.nchunk * BM + (size_t)chunk * BM + row) * Kp;
@@ -713,7 +646,6 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
-  if (csz > 1) cluster_sync_all();
 }
 
 }  // namespace train

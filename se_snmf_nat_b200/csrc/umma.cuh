@@ -71,6 +71,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, 
       "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
 // the same box lands at the same shared-memory offset of every CTA in `mask`, and completes bytes on the barrier at the
 // same offset in each of them
 __device__ __forceinline__ void tma_load_2d_mc(void* smem, const CUtensorMap* map, uint64_t* bar, int x, int y, uint16_t mask) {

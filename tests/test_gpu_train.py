@@ -70,10 +70,10 @@ def test_iterations_match_oracle(api, O, F, K, T, iters):
     np.testing.assert_allclose(out["div"], obj["div"], rtol=2 * TOL)
 
 
-@pytest.mark.parametrize("env", [dict(SNMFNAT_TRAIN_MC="1"), dict(SNMFNAT_TRAIN_V1="1")], ids=["multicast_clusters", "first_generation"])
+@pytest.mark.parametrize("env", [dict(SNMFNAT_TRAIN_V1="1")], ids=["first_generation"])
 def test_other_kernel_variants_match_oracle(api, O, env, monkeypatch):
-    """The switches are read by snmfnat_train_create: TMA-multicast clusters (off by default: measured no gain) and the
-    first-generation 16-row kernels stay selectable and must give the same results."""
+    """The switch is read by snmfnat_train_create: the first-generation 16-row kernels stay selectable and must give
+    the same results."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     F, K, T, iters = 513, 256, 4096, 3
