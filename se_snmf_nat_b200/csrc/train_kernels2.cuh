@@ -88,11 +88,11 @@ struct RingProducer {
 };
 struct RingConsumer {
   uint32_t base_addr; uint64_t* full; uint64_t* empty; uint32_t nu, p;
-  __device__ __forceinline__ uint32_t wait() {   // shared-memory address of the next unit
+  __device__ __forceinline__ uint32_t wait() {   // index of the next unit (its data has landed)
     const uint32_t idx = p % nu;
     umma::mbar_wait(full + idx, (p / nu) & 1);
     umma::tc_fence_after();
-    return base_addr + idx * UNIT;
+    return idx;
   }
   __device__ __forceinline__ void release() {    // free again when the MMAs issued so far have completed
     umma::mma_commit(empty + (p % nu));
@@ -178,7 +178,11 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0 && (int)blockIdx.x < a.ntiles) {
       const uint32_t id2 = idesc_tf32(BM, Kp, 0, 1);
-      const uint32_t hs_a = smem_u32(Hs);
+      // The issuing thread is on the critical path (one thread, dependent integer chains): descriptors are formed once
+      // and then only advanced.  The low 14 bits of a descriptor hold (address >> 4), all addresses are < 256 KB.
+      const uint64_t da0 = smem_desc(smem_u32(Hs), 16, 1024);
+      const uint64_t dk0 = smem_desc(smem_u32(Rg), 16, 1024);                           // K-major tile in unit 0
+      const uint64_t ds0 = smem_desc(smem_u32(Rg), SL * 128, 512, LAYOUT_SW128_32B);    // MN-major slice in unit 0
       RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
       uint32_t n = 0;
       int it = 0;
@@ -195,15 +199,16 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
             const uint32_t id1 = idesc_tf32(BM, half_n(c), 0, 0);
             for (int ks = 0; ks < nkb; ++ks) {
               q0 = clock64();
-              const uint32_t tb = ring.wait();
+              const uint32_t ui = ring.wait();
               p_a += clock64() - q0;
               q0 = clock64();
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t da = smem_desc(hs_a + ks * 16384 + kk * 32, 16, 1024);
-                const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
-                mma_ss(tmem + LAM_COL + HB * b, da, db, id1, (ks > 0) || (kk > 0));
-              }
+              const uint64_t da = da0 + (uint64_t)(ks * (16384 >> 4));
+              const uint64_t db = dk0 + (uint64_t)(ui * (UNIT >> 4));
+              const uint32_t dt = tmem + LAM_COL + HB * b;
+              mma_ss(dt, da, db, id1, ks > 0);
+              mma_ss(dt, da + 2, db + 2, id1, 1);
+              mma_ss(dt, da + 4, db + 4, id1, 1);
+              mma_ss(dt, da + 6, db + 6, id1, 1);
               ring.release();
               p_i1 += clock64() - q0;
             }
@@ -223,13 +228,12 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
               q0 = clock64();
               for (int js = 0; js < half_n(c - 1) / SL; ++js) {
                 const long long q1 = clock64();
-                const uint32_t sb = ring.wait();
+                const uint32_t ui = ring.wait();
                 p_sw += clock64() - q1;
-#pragma unroll
-                for (int j = 0; j < SL / 8; ++j) {
-                  const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
-                  mma_ts(tmem, tmem + LAM_COL + HB * b + SL * js + 8 * j, db, id2, (c > 1) || (js > 0) || (j > 0));
-                }
+                const uint64_t db = ds0 + (uint64_t)(ui * (UNIT >> 4));
+                const uint32_t at = tmem + LAM_COL + HB * b + SL * js;
+                mma_ts(tmem, at, db, id2, (c > 1) || (js > 0));
+                mma_ts(tmem, at + 8, db + (1024 >> 4), id2, 1);
                 ring.release();
               }
               if (c == nh) mma_commit(num_full);
@@ -267,7 +271,7 @@ hphase2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__
         if (row_ok && f0 + 32 <= a.Fm) {
           const float* pv = vcol + (size_t)f0 * a.ldt;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[j] = __ldg(pv + (size_t)j * a.ldt);
+          for (int j = 0; j < 32; ++j) dst[j] = __ldcs(pv + (size_t)j * a.ldt);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) dst[j] = (row_ok && f0 + j < a.Fm) ? __ldg(vcol + (size_t)(f0 + j) * a.ldt) : 0.f;
@@ -524,7 +528,9 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0 && n_my > 0) {
       const uint32_t id4 = idesc_tf32(BM, Kp, 0, 1);
-      const uint32_t wc_a = smem_u32(Wc);
+      const uint64_t da0 = smem_desc(smem_u32(Wc), 16, 1024);
+      const uint64_t dk0 = smem_desc(smem_u32(Rg), 16, 1024);
+      const uint64_t ds0 = smem_desc(smem_u32(Rg), SL * 128, 512, LAYOUT_SW128_32B);
       RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
       mbar_wait(wc_full, 0);
       tc_fence_after();
@@ -533,13 +539,14 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           const uint32_t b = i & 1;
           const uint32_t id3 = idesc_tf32(BM, block_n(i), 0, 0);
           for (int ks = 0; ks < nkb; ++ks) {
-            const uint32_t tb = ring.wait();
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = smem_desc(wc_a + ks * 16384 + kk * 32, 16, 1024);
-              const uint64_t db = smem_desc(tb + kk * 32, 16, 1024);
-              mma_ss(tmem + LAM_COL + HB * b, da, db, id3, (ks > 0) || (kk > 0));
-            }
+            const uint32_t ui = ring.wait();
+            const uint64_t da = da0 + (uint64_t)(ks * (16384 >> 4));
+            const uint64_t db = dk0 + (uint64_t)(ui * (UNIT >> 4));
+            const uint32_t dt = tmem + LAM_COL + HB * b;
+            mma_ss(dt, da, db, id3, ks > 0);
+            mma_ss(dt, da + 2, db + 2, id3, 1);
+            mma_ss(dt, da + 4, db + 4, id3, 1);
+            mma_ss(dt, da + 6, db + 6, id3, 1);
             ring.release();
           }
           mma_commit(lam_full + b);
@@ -550,12 +557,11 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           mbar_wait(r_full + b, (m >> 1) & 1);
           tc_fence_after();
           for (int js = 0; js < block_n(m) / SL; ++js) {
-            const uint32_t sb = ring.wait();
-#pragma unroll
-            for (int j = 0; j < SL / 8; ++j) {
-              const uint64_t db = smem_desc(sb + j * 1024, SL * 128, 512, LAYOUT_SW128_32B);
-              mma_ts(tmem, tmem + LAM_COL + HB * b + SL * js + 8 * j, db, id4, (m > 0) || (js > 0) || (j > 0));
-            }
+            const uint32_t ui = ring.wait();
+            const uint64_t db = ds0 + (uint64_t)(ui * (UNIT >> 4));
+            const uint32_t at = tmem + LAM_COL + HB * b + SL * js;
+            mma_ts(tmem, at, db, id4, (m > 0) || (js > 0));
+            mma_ts(tmem, at + 8, db + (1024 >> 4), id4, 1);
             ring.release();
           }
           if (m == n_my - 1) mma_commit(g_full);
@@ -573,7 +579,7 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       if (f_ok && tf + 32 <= a.T) {
         const float* pv = a.V + (size_t)tf * a.ldv + f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = __ldg(pv + (size_t)j * a.ldv);
+        for (int j = 0; j < 32; ++j) dst[j] = __ldcs(pv + (size_t)j * a.ldv);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[j] = (f_ok && tf + j < a.T) ? __ldg(a.V + (size_t)(tf + j) * a.ldv + f) : 0.f;
