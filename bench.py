@@ -332,7 +332,20 @@ def run_ours(args, rank, world, local_rank):
                         "share_of_step": prof["gain"]["ms"] / prof["total"]["ms"]}
     dom = max(("hsolve", "wsolve", "stft", "istft"), key=lambda k: roof_all[k]["ms_per_step"])
     roofline = dict(roof_all[dom])
-    roofline.update({"kernel": dom + "_kernel", "traffic": None,
+    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read + write of one
+    # launch, divided by the solves of that launch), scaled to the average number of solves per launch of this run
+    traffic = None
+    try:
+        tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+        per_solve = float(tj[dom]["dram_bytes_per_solve"])
+        solves = {"hsolve": stats["hops"], "wsolve": stats["w_solves"]}.get(dom)
+        if solves:
+            traffic = per_solve * solves / roofline["launches"]
+            roofline["traffic_source"] = tj[dom]["source"]
+            roofline["algorithmic_bytes_per_launch"] = float(tj[dom]["algorithmic_bytes_per_solve"]) * solves / roofline["launches"]
+    except Exception:
+        traffic = None
+    roofline.update({"kernel": dom + "_kernel", "traffic": traffic,
                      "peak_source": pk["_fp64_source"] if roofline["unit"] == "TFLOP/s" else pk["_hbm_source"],
                      "note": "fp64 = FP64 FMA pipe (DFMA issue rate); tensor = FP64 tensor-core mma.sync m8n8k4 "
                              "(MEASURED_PEAKS.json holds no FP64 figure, so the FP64 peaks are measured by "
