@@ -400,13 +400,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--groups", type=int, default=int(os.environ.get("SNMFNAT_GROUPS", "3")),
                     help="interleaved slot groups on separate CUDA streams (scheduling only)")
-    ap.add_argument("--workload", default="enhance", choices=["enhance", "train"],
-                    help="enhance = BASELINE.json's headline metric (default); train = configs[3] dictionary training")
+    ap.add_argument("--workload", default="enhance", choices=["enhance", "train", "latency"],
+                    help="enhance = BASELINE.json's headline metric (default); train = configs[3] dictionary training; "
+                         "latency = configs[1]: one stream hop by hop through the per-hop entry, p50/p99 per hop")
     ap.add_argument("--train-frames", type=int, default=1_250_000, help="frames (per GPU for weak scaling)")
     ap.add_argument("--train-k", type=int, default=256)
     ap.add_argument("--train-scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     args.warmup_ref = min(args.warmup, 1)
+    args.warmup_latency = min(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -422,6 +424,9 @@ def main():
         if args.workload == "train":
             import bench_train
             bench_train.run(args, rank, world, local_rank, ClockSampler, measured_peaks)
+        elif args.workload == "latency":
+            import bench_latency
+            bench_latency.run(args, rank, world, local_rank, ClockSampler)
         else:
             run_ours(args, rank, world, local_rank)
     finally:
