@@ -161,7 +161,12 @@ def run(args, rank, world, local_rank, ClockSampler, measured_peaks):
                        "(training data is loaded once and stays resident, as in the reference's sparse_nmf call)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                     "traffic": None, "kernel": "hphase_kernel + wphase_kernel (tcgen05 tf32)",
+                     "traffic": (578e6 + 481e6) * (T / 151552.0),
+                     "traffic_source": "dram__bytes_read+write of hphase2_kernel (578 MB) and wphase2_kernel (481 MB) per "
+                                       "151 552 frames from profiles/r01_train_{h,w}phase2_ncu_full.txt, scaled to the frames "
+                                       "per GPU of this run; algorithmic minimum per iteration ~ (2 V + 4 H) = "
+                                       "(2*F + 4*Kp) * 4 B per frame",
+                     "kernel": "hphase2_kernel + wphase2_kernel (tcgen05 tf32)",
                      "work_per_iteration_per_gpu": flop_iter / world,
                      "peak_source": "TF32 dense = half of the measured sustained bf16 cuBLAS rate in MEASURED_PEAKS.json "
                                     "(no TF32 figure is measured by the driver)"},
