@@ -858,6 +858,14 @@ struct WfLayout {
   }
 };
 
+// 8-byte asynchronous global -> shared copy; `valid == false` writes zero without reading
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
@@ -934,23 +942,10 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   // local row index inside Vs: tiles 0..TPC-1 -> rows 0..8 TPC-1, leftover tile -> the 8 rows after them
   const int vrow = tile_local * 8 + g;
 
-  // ---- stage the log table, V slice (v = max(v, flr), pad = flr), W fragments ----
-  if (tid < 128) tab[tid] = log_tab[tid];
-  if (VSMEM) {
-    for (int t = warp; t < NP; t += WARPS)
-      for (int r = lane; r < L.VROWS; r += 32) {
-        int fr_ = row0 + r;
-        bool ok;
-        if (r < TPC * 8) ok = fr_ < NFT * 8;
-        else {
-          fr_ = NFT * 8 + (r - TPC * 8);
-          ok = (rank == CL - 1) && fr_ < F;
-        }
-        double x = flr;
-        if (ok && t < n) x = fmax(Vg[(size_t)t * LDF + fr_], flr);                // sparse_nmf.m:169
-        Vs[(size_t)t * VS + r] = x;
-      }
-  }
+  // ---- staging.  Everything that comes from HBM is requested up front so that the latencies overlap: the W
+  //      fragments (registers; two dependent loads), then the V slice and the raw history activations as asynchronous
+  //      copies straight into shared memory (padding = 0; v = max(v, flr) is applied where V is read, sparse_nmf.m:169;
+  //      H is scaled by the column norms in place once they are known) ----
   double w[KT][2], gacc[KT][2];
 #pragma unroll
   for (int j = 0; j < KT; ++j)
@@ -962,6 +957,29 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       w[j][e] = x;
       gacc[j][e] = 0.0;
     }
+  if (tid < 128) tab[tid] = log_tab[tid];
+  if (VSMEM) {
+    for (int t = warp; t < NP; t += WARPS)
+      for (int r = lane; r < L.VROWS; r += 32) {
+        int fr_ = row0 + r;
+        bool ok;
+        if (r < TPC * 8) ok = fr_ < NFT * 8;
+        else {
+          fr_ = NFT * 8 + (r - TPC * 8);
+          ok = (rank == CL - 1) && fr_ < F;
+        }
+        ok = ok && t < n;
+        cp_async8(Vs + (size_t)t * VS + r, Vg + (ok ? (size_t)t * LDF + fr_ : 0), ok);
+      }
+  }
+  for (int k = warp; k < KMAX; k += WARPS) {
+    const bool kv = k < Ru;
+    const int src = kv ? idx_up[k] : 0;
+    for (int t = lane; t < NP; t += 32) {
+      const bool ok = kv && t < n;
+      cp_async8(Hs + (size_t)k * HSd + t, Adb + (ok ? (size_t)t * R_a + src : 0), ok);
+    }
+  }
 
   // per-warp partial of a per-column quantity -> red[which][warp][k]
   auto warp_partial = [&](int which, auto&& f) {
@@ -1030,18 +1048,13 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   for (int j = 0; j < KT; ++j)
 #pragma unroll
     for (int e = 0; e < 2; ++e) w[j][e] = w[j][e] / wn_s[8 * j + 2 * tg + e];   // :159
-  // H = init_h .* wn (:160), zero padded; row sums (constant over the solve)
+  // H = init_h .* wn (:160), zero padded (each thread scales what it copied itself); row sums (constant over the solve)
+  cp_async_wait_all();
   for (int k = warp; k < KMAX; k += WARPS) {
-    const bool kv = k < Ru;
-    const int src = kv ? idx_up[k] : 0;
     const double wn = wn_s[k];
-    for (int t = lane; t < NP; t += 32) {
-      double x = 0.0;
-      if (kv && t < n) x = Adb[(size_t)t * R_a + src] * wn;
-      Hs[(size_t)k * HSd + t] = x;
-    }
+    for (int t = lane; t < NP; t += 32) Hs[(size_t)k * HSd + t] *= wn;
   }
-  __syncthreads();
+  __syncthreads();   // also publishes every thread's part of the V slice
   if (tid < KMAX) {
     double s = 0.0;
     for (int t = 0; t < n; ++t) s += Hs[(size_t)tid * HSd + t];
@@ -1091,7 +1104,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const double lam = fmax((q & 1) ? c1[q >> 1] : c0[q >> 1], flr);                 // :243
-        const double v = VSMEM ? vbase[(size_t)(n0 + 4 * tg + q) * VS] : vcur[q];
+        const double v = VSMEM ? fmax(vbase[(size_t)(n0 + 4 * tg + q) * VS], flr) : vcur[q];
         const double r = v * fast_rcp(lam);
         if (want_cost) cacc += fma(v, fast_log(r, tab), lam - v);                         // :250
         rt[q] = r;
