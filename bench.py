@@ -347,6 +347,10 @@ def run_ours(args, rank, world, local_rank):
         traffic = None
     roofline.update({"kernel": dom + "_kernel", "traffic": traffic,
                      "peak_source": pk["_fp64_source"] if roofline["unit"] == "TFLOP/s" else pk["_hbm_source"],
+                     "structural_ceiling": {
+                         "frac_of_peak": 0.25, "why": "both mat-vecs of an H-solve iteration read the FP64 basis slice from "
+                         "shared memory: 8 B per FMA at 128 B/clk/SM = 16 FMA/clk/SM against the pipe's 64; ncu "
+                         "(profiles/r01_v6_hsolve_fast_ncu_full.txt): the shared-memory pipe is 64 % busy"} if dom == "hsolve" else None,
                      "note": "fp64 = FP64 FMA pipe (DFMA issue rate); tensor = FP64 tensor-core mma.sync m8n8k4 "
                              "(MEASURED_PEAKS.json holds no FP64 figure, so the FP64 peaks are measured by "
                              "tools/peaks_fp64); achieved = SURVEY.md 8(d) algorithmic flops / CUDA-event time"})
