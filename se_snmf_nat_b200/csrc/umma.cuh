@@ -78,15 +78,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
       "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
-// the same box lands at the same shared-memory offset of every CTA in `mask`, and completes bytes on the barrier at the
-// same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mc(void* smem, const CUtensorMap* map, uint64_t* bar, int x, int y, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], "
-      "[%2], %3;" ::"r"(smem_u32(smem)),
-      "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(x), "r"(y)
-      : "memory");
-}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
                "r"(smem_u32(smem)), "r"(x), "r"(y)
@@ -203,28 +194,6 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-
-// the same, arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-// plain arrive on the barrier at this offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ uint32_t to_tf32_rn(float x) {
