@@ -312,6 +312,7 @@ void launch_wphase2(snmfnat_train* t, int hbuf) {
   a.nchunk = t->nchunk; a.ngroups = t->ngroups; a.nblocks = t->nblocks_w; a.ldv = t->ldv; a.T = t->T;
   a.V = t->V.p; a.Gpart = t->Gpart.p;
   a.nu = t->nu;
+  a.probe = (t->iters_done == 0 && t->dbg_w.p) ? 1 : 0;
   const int grid = t->nchunk * t->ngroups, cw = t->cur_w;
   wphase2_kernel<<<grid, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mW128[cw], t->mH128[hbuf],
                                                                                        t->mHm16[hbuf], a);

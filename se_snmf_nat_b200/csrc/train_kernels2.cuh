@@ -51,6 +51,7 @@ struct WPhase2Args {
   const float* V;       // [T][ldv]
   float* Gpart;         // [ngroups][nchunk*128][Kp]
   int nu;
+  int probe;            // print the MMA issuer's wait/issue clocks of CTA 0 (diagnostics)
 };
 
 __host__ __device__ constexpr size_t phase2_smem_bytes(int nkb, int nu) {
@@ -534,12 +535,16 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       RingConsumer ring{smem_u32(Rg), u_full, u_empty, (uint32_t)nu, 0u};
       mbar_wait(wc_full, 0);
       tc_fence_after();
+      long long p_a = 0, p_i1 = 0, p_r = 0, p_i2 = 0, p_sw = 0, q0, p_t0 = clock64();
       for (int i = 0; i <= n_my; ++i) {
         if (i < n_my) {  // Lambda(i) = W_rows * H'_block(i)'
           const uint32_t b = i & 1;
           const uint32_t id3 = idesc_tf32(BM, block_n(i), 0, 0);
           for (int ks = 0; ks < nkb; ++ks) {
+            q0 = clock64();
             const uint32_t ui = ring.wait();
+            p_a += clock64() - q0;
+            q0 = clock64();
             const uint64_t da = da0 + (uint64_t)(ks * (16384 >> 4));
             const uint64_t db = dk0 + (uint64_t)(ui * (UNIT >> 4));
             const uint32_t dt = tmem + LAM_COL + HB * b;
@@ -548,25 +553,36 @@ wphase2_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             mma_ss(dt, da + 4, db + 4, id3, 1);
             mma_ss(dt, da + 6, db + 6, id3, 1);
             ring.release();
+            p_i1 += clock64() - q0;
           }
           mma_commit(lam_full + b);
         }
         if (i >= 1) {  // G += R(i-1) * H'_block(i-1)
           const int m = i - 1;
           const uint32_t b = m & 1;
+          q0 = clock64();
           mbar_wait(r_full + b, (m >> 1) & 1);
+          p_r += clock64() - q0;
           tc_fence_after();
+          q0 = clock64();
           for (int js = 0; js < block_n(m) / SL; ++js) {
+            const long long q1 = clock64();
             const uint32_t ui = ring.wait();
+            p_sw += clock64() - q1;
             const uint64_t db = ds0 + (uint64_t)(ui * (UNIT >> 4));
             const uint32_t at = tmem + LAM_COL + HB * b + SL * js;
             mma_ts(tmem, at, db, id4, (m > 0) || (js > 0));
             mma_ts(tmem, at + 8, db + (1024 >> 4), id4, 1);
             ring.release();
           }
+          p_i2 += clock64() - q0;
           if (m == n_my - 1) mma_commit(g_full);
         }
       }
+      if (a.probe && blockIdx.x == 0)
+        printf("wphase2 probe (MMA issuer, CTA 0; ring %d units, grid %d): total %lld clk, %d blocks | wait K tiles %lld, "
+               "issue MMA1 %lld, wait r_full %lld, MMA2 (issue + slice waits) %lld of which slice waits %lld\n",
+               nu, (int)gridDim.x, clock64() - p_t0, n_my, p_a, p_i1, p_r, p_i2, p_sw);
     }
   } else {
     const int e = (warp - 2) >> 2, q = warp & 3;
