@@ -410,25 +410,87 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
     st.h_iters[slot] = it;
     st.h_cost[slot] = cost;
   }
-  for (int part = 0; part < 2; ++part) {
-    __syncthreads();
-    if (tid < R) {
-      // activations for the un-normalised basis (bnmf_sep_event_RT_IS16.m:174,197), restricted to the class
-      const double x = ((tid < R1) == (part == 0)) ? h_fin * wn_r : 0.0;
-      h_s[tid] = x;
-      hp_s[(tid & 7) * HF_HP + (tid >> 3)] = x;
+  // Both reconstructions in ONE pass over the resident basis: X_hat = B_x A_x sums the columns k < R1, D_hat = B_d A_d the
+  // others (bnmf_sep_event_RT_IS16.m:174,197).  Each column feeds the accumulators of its own class only, in the same
+  // order as a pass with the other class zeroed would, so the sums are bit-identical to two separate passes.
+  __syncthreads();
+  if (tid < R) {
+    const double x = h_fin * wn_r;   // activations for the un-normalised basis
+    h_s[tid] = x;
+    hp_s[(tid & 7) * HF_HP + (tid >> 3)] = x;
+  }
+  __syncthreads();
+  double* lam_d = recv;              // 4 partial groups of D_hat (the exchange buffers are idle after the last wait)
+  {
+    double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+    const double* base = Ws + rq * 32 + ((2 * l16) ^ (kg << 1));
+    const double* hp = hp_s + kg * HF_HP;
+    int k = kg, j = 0;
+#pragma unroll 4
+    for (; k + 8 < R; k += 16, j += 2) {
+      const double2 hh = *reinterpret_cast<const double2*>(hp + j);
+      const double2 w0 = *reinterpret_cast<const double2*>(base + (size_t)k * HF_ROWS);
+      const double2 w1 = *reinterpret_cast<const double2*>(base + (size_t)(k + 8) * HF_ROWS);
+      const double hx0 = k < R1 ? hh.x : 0.0, hd0 = k < R1 ? 0.0 : hh.x;
+      const double hx1 = k + 8 < R1 ? hh.y : 0.0, hd1 = k + 8 < R1 ? 0.0 : hh.y;
+      x0 = fma(w0.x, hx0, x0);
+      x1 = fma(w0.y, hx0, x1);
+      d0 = fma(w0.x, hd0, d0);
+      d1 = fma(w0.y, hd0, d1);
+      y0 = fma(w1.x, hx1, y0);
+      y1 = fma(w1.y, hx1, y1);
+      e0 = fma(w1.x, hd1, e0);
+      e1 = fma(w1.y, hd1, e1);
     }
-    __syncthreads();
-    lambda_pass();
-    __syncthreads();
-    double* dst = (part == 0 ? st.Xhat : st.Dhat) + (size_t)slot * LDF;
+    if (k < R) {
+      const double h0 = hp[j];
+      const double2 w0 = *reinterpret_cast<const double2*>(base + (size_t)k * HF_ROWS);
+      const double hx0 = k < R1 ? h0 : 0.0, hd0 = k < R1 ? 0.0 : h0;
+      x0 = fma(w0.x, hx0, x0);
+      x1 = fma(w0.y, hx0, x1);
+      d0 = fma(w0.x, hd0, d0);
+      d1 = fma(w0.y, hd0, d1);
+    }
+    x0 += y0; x1 += y1; d0 += e0; d1 += e1;
+    x0 += __shfl_xor_sync(0xffffffffu, x0, 16);
+    x1 += __shfl_xor_sync(0xffffffffu, x1, 16);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 16);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
+    if (half == 0) {
+      *reinterpret_cast<double2*>(lam_part + kp * HF_ROWS + rq * 32 + 2 * l16) = make_double2(x0, x1);
+      *reinterpret_cast<double2*>(lam_d + kp * HF_ROWS + rq * 32 + 2 * l16) = make_double2(d0, d1);
+    }
+    if (tail_rank && warp < E) {  // tail row `warp`: lanes over atoms
+      double sx = 0.0, sd = 0.0;
+      for (int kk = lane; kk < R; kk += 32) {
+        const double t = Wt[(size_t)warp * R + kk], hv = h_s[kk];
+        sx = fma(t, kk < R1 ? hv : 0.0, sx);
+        sd = fma(t, kk < R1 ? 0.0 : hv, sd);
+      }
+      sx = warp_sum(sx);
+      sd = warp_sum(sd);
+      if (lane == 0) {
+        misc[16 + warp] = sx;
+        misc[24 + warp] = sd;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    double* dx = st.Xhat + (size_t)slot * LDF;
+    double* dd = st.Dhat + (size_t)slot * LDF;
     if (tid < HF_ROWS) {
-      double s = 0.0;
+      double sx = 0.0, sd = 0.0;
 #pragma unroll
-      for (int q = 0; q < HF_KG / 2; ++q) s += lam_part[q * HF_ROWS + tid];
-      dst[f0 + tid] = s;
+      for (int q = 0; q < HF_KG / 2; ++q) {
+        sx += lam_part[q * HF_ROWS + tid];
+        sd += lam_d[q * HF_ROWS + tid];
+      }
+      dx[f0 + tid] = sx;
+      dd[f0 + tid] = sd;
     } else if (tail_rank && tid < HF_ROWS + E) {
-      dst[HF_CL * HF_ROWS + tid - HF_ROWS] = misc[16 + tid - HF_ROWS];
+      dx[HF_CL * HF_ROWS + tid - HF_ROWS] = misc[16 + tid - HF_ROWS];
+      dd[HF_CL * HF_ROWS + tid - HF_ROWS] = misc[24 + tid - HF_ROWS];
     }
   }
   cluster.sync();  // nobody may exit while a peer can still read its exchange buffers
