@@ -184,30 +184,43 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
   const double* __restrict__ V = fr.Ym + (size_t)frame * LDF;
   const double flr = sc.flr;
 
-  // ---- stage W (swizzled), partial column sums / sums of squares over this CTA's rows ----
-  for (int k = warp; k < R; k += HF_WARPS) {
-    const double* src = (k < R1 ? W1 + (size_t)k * LDF : W2 + (size_t)(k - R1) * LDF);
-    double s1 = 0.0, s2 = 0.0;
-    const int sw = (k & 7) << 1;
+  // ---- stage W (swizzled), partial column sums / sums of squares over this CTA's rows.  Four columns per step: their 16
+  //      (+ tail) loads are in flight together, the private half of the basis comes from HBM ----
+  constexpr int SC = 4;
+  for (int k0 = warp; k0 < R; k0 += SC * HF_WARPS) {
+    double x[SC][HF_ROWS / 32], xt[SC];
 #pragma unroll
-    for (int j = 0; j < HF_ROWS / 32; ++j) {
-      const int f = lane + 32 * j;
-      const double x = src[f0 + f];
-      Ws[(size_t)k * HF_ROWS + (f ^ sw)] = x;
-      s1 += x;
-      s2 = fma(x, x, s2);
+    for (int c = 0; c < SC; ++c) {
+      const int k = k0 + c * HF_WARPS;
+      const double* src = (k < R1 ? W1 + (size_t)k * LDF : W2 + (size_t)(k - R1) * LDF);
+#pragma unroll
+      for (int j = 0; j < HF_ROWS / 32; ++j) x[c][j] = (k < R) ? src[f0 + lane + 32 * j] : 0.0;
+      xt[c] = (k < R && tail_rank && lane < E) ? src[HF_CL * HF_ROWS + lane] : 0.0;
     }
-    if (tail_rank && lane < E) {
-      const double x = src[HF_CL * HF_ROWS + lane];
-      Wt[(size_t)lane * R + k] = x;
-      s1 += x;
-      s2 = fma(x, x, s2);
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      xch[k] = s2;  // buffer 0 carries [sumsq | sum] for the normalisation exchange (R + 8 >= ... uses both buffers)
-      xch[L.XN + k] = s1;
+#pragma unroll
+    for (int c = 0; c < SC; ++c) {
+      const int k = k0 + c * HF_WARPS;
+      if (k >= R) break;
+      double s1 = 0.0, s2 = 0.0;
+      const int sw = (k & 7) << 1;
+#pragma unroll
+      for (int j = 0; j < HF_ROWS / 32; ++j) {
+        const int f = lane + 32 * j;
+        Ws[(size_t)k * HF_ROWS + (f ^ sw)] = x[c][j];
+        s1 += x[c][j];
+        s2 = fma(x[c][j], x[c][j], s2);
+      }
+      if (tail_rank && lane < E) {
+        Wt[(size_t)lane * R + k] = xt[c];
+        s1 += xt[c];
+        s2 = fma(xt[c], xt[c], s2);
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        xch[k] = s2;  // buffer 0 carries [sumsq | sum] for the normalisation exchange (R + 8 >= ... uses both buffers)
+        xch[L.XN + k] = s1;
+      }
     }
   }
   for (int f = tid; f < HF_ROWS + (tail_rank ? E : 0); f += HF_THREADS)
