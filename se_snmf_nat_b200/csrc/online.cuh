@@ -97,10 +97,6 @@ void launch_wsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& s
 bool hsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d);
 void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                         const FrameArrays& fr, const double* h_init, int n_active, int g_step);
-// register-resident H-solve (online_reg.cu): 8-CTA clusters, the basis tile of every lane stays in registers
-bool hsolve_reg_supported(snmfnat_ctx* ctx, const OnlineDims& d);
-void launch_hsolve_reg(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
-                       const FrameArrays& fr, const double* h_init, int n_active, int g_step);
 bool wsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d);
 void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                         const TraceArrays* tr, int n_active, int g_step);
@@ -114,9 +110,6 @@ void launch_mel_hist(snmfnat_ctx* ctx, const OnlineDims& d, const SlotState& st,
                      double* lam_blk_mel, int n_active, int g_step);
 // SNMFNAT_FORCE_GENERIC=1 in the environment disables the fast paths (used by the parity tests)
 bool force_generic();
-// SNMFNAT_HSOLVE=reg selects the experimental register-resident H-solve (online_reg.cu) instead of the shared-memory
-// one; measured slower on B200 (profiles/r01_hsolve_reg_ncu_full.txt), kept selectable and parity-tested
-bool prefer_reg_hsolve();
 // shared-memory footprints (bytes) so that callers can reject configurations that do not fit
 size_t hsolve_smem_bytes(const OnlineDims& d);
 size_t wsolve_smem_bytes(const OnlineDims& d);

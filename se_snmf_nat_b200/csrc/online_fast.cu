@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 #include <cmath>
 #include "online.cuh"
+#include "online_dev.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -26,34 +27,6 @@ namespace snmfnat {
 // =====================================================================================================
 // shared helpers
 // =====================================================================================================
-__device__ __forceinline__ double fast_rcp(double x) {  // x > 0, normal.  <= 1 ulp after two Newton steps
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
-}
-
-// log(x) for positive normal x: x = 2^e * m, m in [1,2); c = centre of m's 1/128 bucket; z = m/c - 1, |z| <= 2^-8;
-// log x = e ln2 + log c + log1p(z) with a degree-7 series.  tab[i] = {1/c_i, log c_i}.
-__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
-  const int hi = __double2hiint(x);
-  const int e = (hi >> 20) - 1023;
-  const int idx = (hi >> 13) & 127;
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-  const double2 t = tab[idx];
-  const double z = fma(m, t.x, -1.0);
-  double p = fma(z, 1.0 / 7.0, -1.0 / 6.0);
-  p = fma(p, z, 0.2);
-  p = fma(p, z, -0.25);
-  p = fma(p, z, 1.0 / 3.0);
-  p = fma(p, z, -0.5);
-  const double l = fma(p, z * z, z);
-  return fma((double)e, 0.693147180559945309417232, t.y + l);
-}
-
 __global__ void log_table_kernel(double2* tab) {
   const int i = threadIdx.x;
   if (i < 128) {
@@ -63,7 +36,7 @@ __global__ void log_table_kernel(double2* tab) {
 }
 
 static double2* g_log_tab[64] = {nullptr};
-static const double2* log_table(snmfnat_ctx* ctx) {
+const double2* log_table(snmfnat_ctx* ctx) {
   const int dev = ctx->device;
   SN_REQUIRE(dev >= 0 && dev < 64, SNMFNAT_EINVAL, "device index out of range");
   if (!g_log_tab[dev]) {
@@ -114,33 +87,6 @@ __host__ __device__ inline HfLayout hf_layout(int F, int R) {
   L.off_bar = o;  o += 2;                          // 2 mbarriers
   L.bytes = o * sizeof(double);
   return L;
-}
-
-// mbarrier + st.async (push over distributed shared memory, completion counted in bytes on the receiver's barrier)
-__device__ __forceinline__ unsigned hf_mapa(unsigned addr, unsigned rank) {
-  unsigned r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void hf_st_async(unsigned raddr, double v, unsigned rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
-               :: "r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
-}
-__device__ __forceinline__ void hf_mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void hf_mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void hf_mbar_wait(unsigned bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
 }
 
 __global__ void __cluster_dims__(HF_CL, 1, 1) __launch_bounds__(HF_THREADS, 1)
@@ -509,11 +455,6 @@ hsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr,
   cluster.sync();  // nobody may exit while a peer can still read its exchange buffers
 }
 
-static bool hsolve_use_c8();
-static bool hsolve_c8_supported(snmfnat_ctx* ctx, const OnlineDims& d);
-static void launch_hsolve_c8(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
-                             const FrameArrays& fr, const double* h_init, int n_active, int g_step);
-
 bool hsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
   const int E = d.F - HF_CL * HF_ROWS;
   if (E < 0 || E > 8) return false;
@@ -523,375 +464,12 @@ bool hsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
 
 void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                         const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
-  if (hsolve_use_c8() && hsolve_c8_supported(ctx, d)) {
-    launch_hsolve_c8(ctx, d, sc, st, fr, h_init, n_active, g_step);
-    return;
-  }
   const HfLayout L = hf_layout(d.F, d.R);
   SN_CUDA(cudaFuncSetAttribute(hsolve_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
   hsolve_fast_kernel<<<dim3(HF_CL * n_active), dim3(HF_THREADS), L.bytes, ctx->stream>>>(d, sc, st, fr, h_init, g_step,
                                                                                          log_table(ctx));
   count_launch(ctx);
   check_launch(ctx, "hsolve_fast_kernel");
-}
-
-// =====================================================================================================
-// H-solve, two CTAs per SM: 8-CTA clusters, 64 rows of W per CTA (F = 512 + E)
-// =====================================================================================================
-// Same mat-vec passes and swizzle as hsolve_fast_kernel, but the basis slice of a CTA is 102 KB, so TWO CTAs (of
-// different streams) share an SM: the passes of one fill the shared-memory pipe while the other sits in a barrier or
-// in the cluster exchange.  To fit, the exchange is a reduce-scatter + all-gather instead of an all-to-all:
-//   (1) every lane pushes its partial of g_k to the ONE CTA that owns atom k (rank k / AP), cost partials go to all
-//   (2) the owner adds the 8 partials in rank order, updates h_k and pushes it into the h vector of all 8 CTAs
-// (st.async + mbarrier byte counts, no cluster barrier).  Every CTA sees bit-identical h and cost, hence the same stop.
-constexpr int H8_THREADS = 256;
-constexpr int H8_WARPS = 8;
-constexpr int H8_CL = 8;
-constexpr int H8_ROWS = 64;
-constexpr int H8_KG = 8;
-constexpr int H8_HP = 34;
-
-struct H8Layout {
-  int E, XN, AP, RS;
-  size_t off_W, off_Wt, off_v, off_r, off_dph, off_hp, off_lam, off_recv, off_misc, off_bar, bytes;
-};
-__host__ __device__ inline H8Layout h8_layout(int F, int R) {
-  H8Layout L;
-  L.E = F - H8_CL * H8_ROWS;
-  L.XN = R + 2;
-  L.AP = (R + H8_CL - 1) / H8_CL;    // atoms owned by one rank
-  L.RS = L.AP + 2;                   // receive row: [AP] partials of the owned atoms, cost partial, sum(h)
-  size_t o = 0;
-  L.off_W = o;    o += (size_t)R * H8_ROWS;
-  L.off_Wt = o;   o += (size_t)(L.E > 0 ? L.E : 0) * R;
-  o = (o + 1) & ~(size_t)1;
-  L.off_v = o;    o += H8_ROWS + 8;
-  L.off_r = o;    o += H8_ROWS + 8;
-  L.off_dph = o;  o += R;
-  o = (o + 1) & ~(size_t)1;
-  L.off_hp = o;   o += (size_t)H8_KG * H8_HP;
-  // lam [4][64] and recv [2][CL][RS] are contiguous: before the loop the same region is the [2][XN] buffer of the
-  // one-off normalisation exchange
-  L.off_lam = o;  o += (size_t)(H8_KG / 2) * H8_ROWS;
-  L.off_recv = o; o += 2 * (size_t)H8_CL * L.RS;
-  if (o - L.off_lam < 2 * (size_t)L.XN) o = L.off_lam + 2 * (size_t)L.XN;
-  o = (o + 1) & ~(size_t)1;
-  L.off_misc = o; o += 32;
-  L.off_bar = o;  o += 3;            // mbarriers: partials (double-buffered), h
-  L.bytes = o * sizeof(double);
-  return L;
-}
-
-__global__ void __cluster_dims__(H8_CL, 1, 1) __launch_bounds__(H8_THREADS, 2)
-hsolve_c8_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, const double* __restrict__ h_init,
-                 int g_step, const double2* __restrict__ log_tab) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int slot = d.slot0 + (int)(blockIdx.x / H8_CL) * d.slot_stride;
-  const int l = g_step + 1 - st.l_offset[slot];
-  if (l < 1 || l > st.n_hops[slot]) return;  // uniform over the cluster
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int F = d.F, R = d.R, R1 = d.R_x, LDF = d.LDF;
-  const H8Layout L = h8_layout(F, R);
-  const int E = L.E, AP = L.AP, RS = L.RS;
-  const bool tail_rank = (rank == H8_CL - 1) && E > 0;
-  const int f0 = rank * H8_ROWS;
-  const int n_own = max(0, min(AP, R - rank * AP));
-
-  extern __shared__ __align__(1024) double smem[];
-  double* Ws = smem + L.off_W;
-  double* Wt = smem + L.off_Wt;       // [E][R] tail rows (last rank only)
-  double* v_s = smem + L.off_v;       // [64 + E]
-  double* r_s = smem + L.off_r;       // ratio v./lambda
-  double* dph_s = smem + L.off_dph;   // 1/wn per atom (staging of the column scaling)
-  double* hp_s = smem + L.off_hp;     // h, atom k at (k & 7) * HP + (k >> 3)
-  double* lam_part = smem + L.off_lam;
-  double* xch = smem + L.off_lam;     // [2][XN] normalisation exchange (aliases lam_part + recv; dead before the loop)
-  double* recv = smem + L.off_recv;   // [2][CL][RS]
-  double* misc = smem + L.off_misc;   // [16..23] lambda of the tail rows
-  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem + L.off_bar);
-  const unsigned barB = bar0 + 16u;
-  if (tid == 0) {
-    hf_mbar_init(bar0, 1);
-    hf_mbar_init(bar0 + 8, 1);
-    hf_mbar_init(barB, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  auto hidx = [](int k) { return (k & 7) * H8_HP + (k >> 3); };
-
-  const double* __restrict__ W1 = st.Bx;
-  const double* __restrict__ W2 = st.Bd[st.bd_sel[slot]] + (size_t)slot * d.R_d * LDF;
-  const long long frame = st.frame_base[slot] + g_step;
-  const double* __restrict__ V = fr.Ym + (size_t)frame * LDF;
-  const double flr = sc.flr;
-
-  // ---- stage W (swizzled), partial column sums / sums of squares over this CTA's rows ----
-  for (int k = warp; k < R; k += H8_WARPS) {
-    const double* src = (k < R1 ? W1 + (size_t)k * LDF : W2 + (size_t)(k - R1) * LDF);
-    double s1 = 0.0, s2 = 0.0;
-    const int sw = (k & 7) << 1;
-#pragma unroll
-    for (int j = 0; j < H8_ROWS / 32; ++j) {
-      const int f = lane + 32 * j;
-      const double x = src[f0 + f];
-      Ws[(size_t)k * H8_ROWS + (f ^ sw)] = x;
-      s1 += x;
-      s2 = fma(x, x, s2);
-    }
-    if (tail_rank && lane < E) {
-      const double x = src[H8_CL * H8_ROWS + lane];
-      Wt[(size_t)lane * R + k] = x;
-      s1 += x;
-      s2 = fma(x, x, s2);
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      xch[k] = s2;
-      xch[L.XN + k] = s1;
-    }
-  }
-  for (int f = tid; f < H8_ROWS + (tail_rank ? E : 0); f += H8_THREADS)
-    v_s[f] = fmax(V[f < H8_ROWS ? f0 + f : H8_CL * H8_ROWS + (f - H8_ROWS)], flr);  // sparse_nmf.m:169
-  cluster.sync();
-
-  // ---- column norms, h scaling (sparse_nmf.m:157-160), denominators (:192-193) ----
-  double wn_r = 1.0;      // of atom `tid`
-  double own_dph = 0.0;   // reciprocal of the H-update denominator of the OWNED atom rank*AP + tid
-  if (tid < R) {
-    double s2 = 0.0;
-    for (int c = 0; c < H8_CL; ++c) s2 += cluster.map_shared_rank(xch, c)[tid];
-    const double wn = sqrt(s2);
-    wn_r = wn;
-    dph_s[tid] = 1.0 / wn;
-    hp_s[hidx(tid)] = h_init[tid] * wn;
-  }
-  if (tid < n_own) {
-    const int k = rank * AP + tid;
-    double s2 = 0.0, s1 = 0.0;
-    for (int c = 0; c < H8_CL; ++c) {
-      const double* rx = cluster.map_shared_rank(xch, c);
-      s2 += rx[k];
-      s1 += rx[L.XN + k];
-    }
-    own_dph = 1.0 / fmax(s1 / sqrt(s2) + sc.sparsity, flr);   // :192-193
-  }
-  cluster.sync();  // everyone has read the exchange buffers before the region is reused; publishes dph_s / hp_s
-  for (int k = warp; k < R; k += H8_WARPS) {
-    const double inv = dph_s[k];
-#pragma unroll
-    for (int j = 0; j < H8_ROWS / 32; ++j) {
-      double* p = Ws + (size_t)k * H8_ROWS + lane + 32 * j;
-      *p = *p * inv;
-    }
-    if (tail_rank && lane < E) Wt[(size_t)lane * R + k] = Wt[(size_t)lane * R + k] * inv;
-  }
-  __syncthreads();
-
-  // ---- multiplicative updates ----
-  const int kp = warp & 3, rq = warp >> 2, half = lane >> 4, l16 = lane & 15;
-  const int kg = kp + 4 * half;
-  auto lambda_pass = [&]() {
-    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    const double* base = Ws + rq * 32 + ((2 * l16) ^ (kg << 1));
-    const double* hp = hp_s + kg * H8_HP;
-    int k = kg, j = 0;
-#pragma unroll 4
-    for (; k + 8 < R; k += 16, j += 2) {
-      const double2 hh = *reinterpret_cast<const double2*>(hp + j);
-      const double2 w0 = *reinterpret_cast<const double2*>(base + (size_t)k * H8_ROWS);
-      const double2 w1 = *reinterpret_cast<const double2*>(base + (size_t)(k + 8) * H8_ROWS);
-      a0 = fma(w0.x, hh.x, a0);
-      a1 = fma(w0.y, hh.x, a1);
-      b0 = fma(w1.x, hh.y, b0);
-      b1 = fma(w1.y, hh.y, b1);
-    }
-    if (k < R) {
-      const double h0 = hp[j];
-      const double2 w0 = *reinterpret_cast<const double2*>(base + (size_t)k * H8_ROWS);
-      a0 = fma(w0.x, h0, a0);
-      a1 = fma(w0.y, h0, a1);
-    }
-    a0 += b0;
-    a1 += b1;
-    a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-    if (half == 0) *reinterpret_cast<double2*>(lam_part + kp * H8_ROWS + rq * 32 + 2 * l16) = make_double2(a0, a1);
-    if (tail_rank && warp < E) {  // tail row `warp`: lanes over atoms
-      double s = 0.0;
-      for (int kk = lane; kk < R; kk += 32) s = fma(Wt[(size_t)warp * R + kk], hp_s[hidx(kk)], s);
-      s = warp_sum(s);
-      if (lane == 0) misc[16 + warp] = s;
-    }
-  };
-  int it = 0;
-  double last_cost = INFINITY, cost = 0.0;
-  for (;;) {
-    lambda_pass();   // (A)
-    __syncthreads();
-    // (R) ratio for the CTA's rows (threads 0..63) and the tail rows (threads 64..64+E)
-    if (warp < 3) {
-      const bool main_row = tid < H8_ROWS;
-      const bool tail_row = tail_rank && tid >= H8_ROWS && tid < H8_ROWS + E;
-      if (main_row || tail_row) {
-        double lam = 0.0;
-        if (main_row) {
-#pragma unroll
-          for (int q = 0; q < H8_KG / 2; ++q) lam += lam_part[q * H8_ROWS + tid];
-        } else {
-          lam = misc[16 + tid - H8_ROWS];
-        }
-        lam = fmax(lam, flr);
-        r_s[tid] = v_s[tid] * fast_rcp(lam);
-        if (main_row) lam_part[tid] = lam; else misc[16 + tid - H8_ROWS] = lam;   // kept for the cost terms
-      }
-    }
-    __syncthreads();
-    // (B) g partial over this CTA's 64 rows, lane <-> atom; pushed to the owner of the atom
-    const int buf = it & 1;
-    const unsigned barA = bar0 + 8u * (unsigned)buf;
-    const unsigned parityA = (unsigned)(it >> 1) & 1u;
-    double* rb = recv + (size_t)buf * H8_CL * RS;
-    const unsigned my_row = (unsigned)__cvta_generic_to_shared(rb + (size_t)rank * RS);
-    if (tid == 0) hf_mbar_expect_tx(barA, (unsigned)((H8_CL * (n_own + 1) + 1) * sizeof(double)));
-    if (warp < H8_WARPS - 1) {
-      const int kB = warp * 32 + lane;
-      if (kB < R) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const unsigned wx = (unsigned)__cvta_generic_to_shared(Ws + (size_t)kB * H8_ROWS) ^ ((unsigned)(kB & 7) << 4);
-        const double2* rp = reinterpret_cast<const double2*>(r_s);
-#pragma unroll 8
-        for (int i = 0; i < H8_ROWS / 2; i += 2) {
-          double2 w0, w1;
-          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w0.x), "=d"(w0.y) : "r"(wx ^ ((unsigned)i << 4)));
-          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w1.x), "=d"(w1.y) : "r"(wx ^ ((unsigned)(i + 1) << 4)));
-          const double2 q0 = rp[i], q1 = rp[i + 1];
-          a0 = fma(w0.x, q0.x, a0);
-          a1 = fma(w0.y, q0.y, a1);
-          a2 = fma(w1.x, q1.x, a2);
-          a3 = fma(w1.y, q1.y, a3);
-        }
-        double g = (a0 + a1) + (a2 + a3);
-        if (tail_rank)
-          for (int e = 0; e < E; ++e) g = fma(Wt[(size_t)e * R + kB], r_s[H8_ROWS + e], g);
-        const int o = kB / AP;
-        hf_st_async(hf_mapa(my_row + 8u * (unsigned)(kB - o * AP), o), g, hf_mapa(barA, o));
-      }
-    } else {
-      // spare warp: sum(h) for the sparsity term (same order on every CTA; stays here) and the KL terms of this CTA's
-      // rows (sparse_nmf.m:250), evaluated while the other warps run phase (B)
-      double s = 0.0;
-      for (int kk = lane; kk < R; kk += 32) s += hp_s[hidx(kk)];
-      s = warp_sum(s);
-      double cterm = 0.0;
-      if (sc.cost_check && it >= 1) {
-#pragma unroll
-        for (int j = 0; j < H8_ROWS / 32; ++j) {
-          const int f = lane + 32 * j;
-          const double v = v_s[f], lam = lam_part[f];
-          cterm += fma(v, fast_log(r_s[f], log_tab), lam - v);
-        }
-        if (tail_rank && lane < E) {
-          const double v = v_s[H8_ROWS + lane], lam = misc[16 + lane];
-          cterm += fma(v, fast_log(r_s[H8_ROWS + lane], log_tab), lam - v);
-        }
-      }
-      cterm = warp_sum(cterm);
-      if (lane == 0) {
-        hf_st_async(hf_mapa(my_row + 8u * (unsigned)(AP + 1), rank), s, hf_mapa(barA, rank));
-#pragma unroll
-        for (int c = 0; c < H8_CL; ++c) hf_st_async(hf_mapa(my_row + 8u * (unsigned)AP, c), cterm, hf_mapa(barA, c));
-      }
-    }
-    hf_mbar_wait(barA, parityA);
-    // (C) owners combine the 8 CTAs in rank order; convergence test (identical on every CTA); h update + all-gather
-    double gk = 0.0;
-    if (tid < n_own)
-      for (int c = 0; c < H8_CL; ++c) gk += rb[(size_t)c * RS + tid];
-    bool stop = false;
-    if (sc.cost_check && it >= 1) {
-      double div = 0.0;
-      for (int c = 0; c < H8_CL; ++c) div += rb[(size_t)c * RS + AP];
-      cost = div + sc.sparsity * rb[(size_t)rank * RS + AP + 1];           // :261
-      if (it > 1 && sc.conv_eps > 0.0) {
-        const double e = fabs(cost - last_cost) / last_cost;             // :274
-        if (e < sc.conv_eps) stop = true;
-      }
-      last_cost = cost;
-    }
-    if (it >= sc.max_iter) stop = true;
-    if (stop) break;
-    if (tid == 0) hf_mbar_expect_tx(barB, (unsigned)(R * sizeof(double)));
-    if (tid < n_own) {
-      const int hi = hidx(rank * AP + tid);
-      const double hn = hp_s[hi] * gk * own_dph;                           // :195
-      const unsigned la = (unsigned)__cvta_generic_to_shared(hp_s + hi);
-#pragma unroll
-      for (int c = 0; c < H8_CL; ++c) hf_st_async(hf_mapa(la, c), hn, hf_mapa(barB, c));
-    }
-    hf_mbar_wait(barB, (unsigned)it & 1u);
-    ++it;
-  }
-
-  // ---- outputs ----
-  __syncthreads();
-  double h_fin = 0.0;
-  if (tid < R) {
-    h_fin = hp_s[hidx(tid)];
-    if (rank == 0) st.A[(size_t)slot * R + tid] = h_fin;
-  }
-  if (rank == 0 && tid == 0) {
-    st.h_iters[slot] = it;
-    st.h_cost[slot] = cost;
-  }
-  for (int part = 0; part < 2; ++part) {
-    __syncthreads();
-    // activations for the un-normalised basis (bnmf_sep_event_RT_IS16.m:174,197), restricted to the class
-    if (tid < R) hp_s[hidx(tid)] = ((tid < R1) == (part == 0)) ? h_fin * wn_r : 0.0;
-    __syncthreads();
-    lambda_pass();
-    __syncthreads();
-    double* dst = (part == 0 ? st.Xhat : st.Dhat) + (size_t)slot * LDF;
-    if (tid < H8_ROWS) {
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < H8_KG / 2; ++q) s += lam_part[q * H8_ROWS + tid];
-      dst[f0 + tid] = s;
-    } else if (tail_rank && tid < H8_ROWS + E) {
-      dst[H8_CL * H8_ROWS + tid - H8_ROWS] = misc[16 + tid - H8_ROWS];
-    }
-  }
-  cluster.sync();  // nobody may exit while a peer can still push into / read from its shared memory
-}
-
-// SNMFNAT_HSOLVE=c8 selects this geometry.  Measured 3 % SLOWER than the one-CTA-per-SM hsolve_fast_kernel on B200
-// (3 529 vs 3 413 ms per 1024-utterance step): the solve is bound by the shared-memory pipe (64 % busy in ncu, broadcast
-// vector loads included), which two co-resident CTAs share, not by latency that a second CTA could hide.  Kept
-// selectable and parity-tested.
-static bool hsolve_use_c8() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SNMFNAT_HSOLVE");
-    v = (e && e[0] == 'c' && e[1] == '8') ? 1 : 0;
-  }
-  return v == 1;
-}
-static bool hsolve_c8_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
-  const int E = d.F - H8_CL * H8_ROWS;
-  if (E < 0 || E > 8) return false;
-  if (d.R > 32 * (H8_WARPS - 1) || d.R < H8_CL) return false;
-  return 2 * (h8_layout(d.F, d.R).bytes + 1024) <= (size_t)ctx->max_smem_optin + 1024;   // two CTAs per SM
-}
-static void launch_hsolve_c8(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
-                             const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
-  const H8Layout L = h8_layout(d.F, d.R);
-  SN_CUDA(cudaFuncSetAttribute(hsolve_c8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-  SN_CUDA(cudaFuncSetAttribute(hsolve_c8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  hsolve_c8_kernel<<<dim3(H8_CL * n_active), dim3(H8_THREADS), L.bytes, ctx->stream>>>(d, sc, st, fr, h_init, g_step,
-                                                                                       log_table(ctx));
-  count_launch(ctx);
-  check_launch(ctx, "hsolve_c8_kernel");
 }
 
 // =====================================================================================================
@@ -1284,17 +862,6 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   if (rank == 0 && tid == 0) st.bd_sel[slot] = sel ^ 1;
 }
 
-// SNMFNAT_WSOLVE=c8 selects the 8-CTA / two-CTAs-per-SM geometry; measured 10 % SLOWER than the default one-CTA-per-SM
-// geometry on B200 (3 498 vs 3 165 ms per 1024-utterance step: H is staged by twice as many CTAs, V comes from L2
-// every iteration, and the FP64 pipe rather than latency bounds the GEMM phase), kept selectable and parity-tested
-static bool wsolve_use_c8() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SNMFNAT_WSOLVE");
-    v = (e && e[0] == 'c' && e[1] == '8') ? 1 : 0;
-  }
-  return v == 1;
-}
 static bool wsolve_geom_ok(const OnlineDims& d, int CL, int TPC) {
   return (d.F + 7) / 8 <= CL * TPC + 1 && d.F / 8 <= CL * TPC;
 }
@@ -1321,15 +888,8 @@ void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScala
   const double2* tab = log_table(ctx);
   TraceArrays t{};
   if (tr) t = *tr;
-  const bool c8 = wsolve_use_c8() && wsolve_geom_ok(d, 8, 8) &&
-                  2 * (WfLayout<8, 8, 8, false>(d.m_a).bytes + 1024) <= (size_t)ctx->max_smem_optin + 1024;
-  if (d.R_a <= 56) {
-    if (c8) launch_wsolve_variant<7, 8, 8, false>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
-    else launch_wsolve_variant<7, 4, 16, true>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
-  } else {
-    if (c8) launch_wsolve_variant<8, 8, 8, false>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
-    else launch_wsolve_variant<8, 4, 16, true>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
-  }
+  if (d.R_a <= 56) launch_wsolve_variant<7, 4, 16, true>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
+  else launch_wsolve_variant<8, 4, 16, true>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
   count_launch(ctx);
   check_launch(ctx, "wsolve_fast_kernel");
 }

@@ -273,22 +273,9 @@ bool force_generic() {
   return v == 1;
 }
 
-bool prefer_reg_hsolve() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SNMFNAT_HSOLVE");
-    v = (e && std::string(e) == "reg") ? 1 : 0;
-  }
-  return v == 1;
-}
-
 void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
   if (n_active <= 0) return;
-  if (!force_generic() && prefer_reg_hsolve() && hsolve_reg_supported(ctx, d)) {
-    launch_hsolve_reg(ctx, d, sc, st, fr, h_init, n_active, g_step);
-    return;
-  }
   if (!force_generic() && hsolve_fast_supported(ctx, d)) {
     launch_hsolve_fast(ctx, d, sc, st, fr, h_init, n_active, g_step);
     return;
