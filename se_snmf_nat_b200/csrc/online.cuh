@@ -67,6 +67,9 @@ struct SlotState {
   const long long* frame_base;  // [S] frame index of (slot, g_step = 0)
   // accumulators
   unsigned long long* stats;    // [8]: hops, h_iters, w_iters, gated, w_solves, w_atoms
+  // multi-stream H-solve (online_ms.cu): norms / sums of the stream-invariant columns, optional launch order of the slots
+  const double* ms_colstat = nullptr;
+  const int* ms_perm = nullptr;
 };
 
 // Per-frame arrays shared by the STFT, the solvers and the ISTFT.
@@ -97,6 +100,15 @@ void launch_wsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& s
 bool hsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d);
 void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                         const FrameArrays& fr, const double* h_init, int n_active, int g_step);
+// multi-stream H-solve (online_ms.cu): S streams per 8-CTA cluster, stream-invariant columns as FP64 tensor-core fragments
+bool hsolve_ms_supported(snmfnat_ctx* ctx, const OnlineDims& d);
+int hsolve_ms_streams();
+void launch_ms_colstat(snmfnat_ctx* ctx, const OnlineDims& d, const double* Bx, const double* Bd_fix, double* colstat);
+void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                      const FrameArrays& fr, const double* h_init, int n_active, int g_step);
+// SNMFNAT_HSOLVE=ms forces the multi-stream kernel for any number of active streams, =single disables it; by default it
+// runs when at least hsolve_ms_streams() streams are active
+int hsolve_ms_mode();
 bool wsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d);
 void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                         const TraceArrays* tr, int n_active, int g_step);

@@ -83,6 +83,21 @@ __device__ __forceinline__ void hf_mbar_wait_bounded(unsigned bar, unsigned pari
   }
 }
 
+// One bulk copy of `bytes` (multiple of 16, 16-byte aligned) from this CTA's shared memory into the shared memory of a CTA
+// of the cluster; the bytes are counted on the RECEIVER's mbarrier (cp.async.bulk, async proxy -> SASS UBLKCP).
+__device__ __forceinline__ void hf_bulk_push(unsigned rdst, unsigned src, unsigned bytes, unsigned rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(rdst), "r"(src), "r"(bytes), "r"(rbar) : "memory");
+}
+// generic-proxy writes to shared memory become visible to the async proxy (call before a barrier that precedes a bulk copy)
+__device__ __forceinline__ void hf_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores.  lane = 4*i + j:  a = A[i][j],  b = B[j][i],  c0/c1 = C[i][2j], C[i][2j+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // the 128-entry {1/c, log c} table of fast_log on the context's device (created on first use)
 const double2* log_table(snmfnat_ctx* ctx);
 

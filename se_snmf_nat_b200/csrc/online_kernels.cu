@@ -273,9 +273,25 @@ bool force_generic() {
   return v == 1;
 }
 
+int hsolve_ms_mode() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("SNMFNAT_HSOLVE");
+    v = !e ? 0 : (std::string(e) == "ms" ? 1 : (std::string(e) == "single" ? -1 : 0));
+  }
+  return v;
+}
+
 void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
   if (n_active <= 0) return;
+  if (!force_generic() && st.ms_colstat && hsolve_ms_supported(ctx, d)) {
+    const int mode = hsolve_ms_mode();
+    if (mode == 1 || (mode == 0 && n_active >= hsolve_ms_streams())) {
+      launch_hsolve_ms(ctx, d, sc, st, fr, h_init, n_active, g_step);
+      return;
+    }
+  }
   if (!force_generic() && hsolve_fast_supported(ctx, d)) {
     launch_hsolve_fast(ctx, d, sc, st, fr, h_init, n_active, g_step);
     return;

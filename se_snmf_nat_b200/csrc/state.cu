@@ -88,6 +88,11 @@ void SlotBuffers::alloc(int S_, const OnlineDims& d_) {
 void SlotBuffers::set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B_d) {
   upload_basis(ctx, B_x, d.F, d.R_x, d.LDF, Bx.p);
   upload_basis(ctx, B_d, d.F, d.R_d, d.LDF, Bd_fix.p);
+  if (hsolve_ms_supported(ctx, d)) {
+    ms_colstat.alloc(2 * 152);
+    launch_ms_colstat(ctx, d, Bx.p, Bd_fix.p, ms_colstat.p);
+    SN_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
 }
 
 void SlotBuffers::set_mel(snmfnat_ctx* ctx, int n1_, const double* B_Mel_x, const double* B_Mel_d, const double* melmat) {
@@ -245,6 +250,7 @@ SlotState SlotBuffers::view() const {
   v.idx_up = idx_up.p; v.idx_rem = idx_rem.p; v.w_iters = w_iters.p; v.err_flag = err_flag.p;
   v.l_offset = l_offset.p; v.n_hops = n_hops.p; v.frame_base = frame_base.p;
   v.stats = stats.p;
+  v.ms_colstat = ms_colstat.p;
   return v;
 }
 

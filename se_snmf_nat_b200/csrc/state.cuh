@@ -25,6 +25,7 @@ struct SlotBuffers {
   int n_utt_ad = 0;   // utterances held in Ad_init
   DevBuf<long long> frame_base;
   DevBuf<unsigned long long> stats;
+  DevBuf<double> ms_colstat;   // norms / sums of the stream-invariant columns (multi-stream H-solve), when supported
 
   // Mel separation mode: Mel-sized bases / history / reconstructions next to the DFT-domain state
   int n1 = 0, LD1 = 0;

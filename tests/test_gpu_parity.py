@@ -146,6 +146,38 @@ def test_chain_mode_carries_the_noise_basis_between_files(api, O, bases, wavs, r
     b.close()
 
 
+def test_multi_stream_hsolve_matches_oracle(api, O, bases, wavs, rng_inputs):
+    """17 ragged utterances in one batch: the multi-stream H-solve (7 streams in lock step per 8-CTA cluster, the 150
+    stream-invariant columns as FP64 tensor-core fragments) runs while >= 7 streams are active, the per-stream kernel
+    afterwards.  Every utterance must match the oracle hop by hop: iteration counts, gates, activations, waveform."""
+    h_init, _ = rng_inputs
+    p = api.default_p()
+    po = O.default_params()
+    rs = np.random.RandomState(11)
+    src = np.concatenate([wavs["M04_in"], wavs["M03_in"]])
+    pcms = []
+    for i in range(17):
+        n = 160 * int(rs.randint(22, 60)) + int(rs.randint(0, 160))
+        o = int(rs.randint(0, len(src) - n))
+        pcms.append(src[o:o + n])
+    ads = np.stack([rs.rand(50, 100) for _ in pcms])
+    b, outs = run_gpu_traced(api, p, pcms, bases, h_init, ads)
+    tot_h = 0
+    for i, pcm in enumerate(pcms):
+        tr = []
+        ref, _ = O.enhance_utterance(pcm, po, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=ads[i], trace=tr)
+        hi = b.trace(i, "h_iters").astype(int)
+        assert np.array_equal(hi, np.array([t["h_iters"] for t in tr])), i
+        assert np.array_equal(b.trace(i, "gated").astype(int), np.array([int(t["gated"]) for t in tr])), i
+        assert np.array_equal(b.trace(i, "w_iters").astype(int), np.array([t["w_iters"] for t in tr])), i
+        A = b.trace(i, "A")
+        assert max(rel_err(tr[k]["A"], A[k]) for k in range(len(tr))) <= SPEC_TOL, i
+        assert np.abs(outs[i].astype(int) - ref.astype(int)).max() <= 1, i
+        tot_h += int(hi.sum())
+    assert b.stats()["h_iters"] == tot_h
+    b.close()
+
+
 def test_stream_groups_do_not_change_results(api, bases, wavs, rng_inputs):
     """snmfnat_batch_set_groups is a scheduling knob: interleaved slot groups on separate CUDA streams give bit-identical
     output (also with chains, whose boundary re-initialisation has to run on the owning group's stream)."""
@@ -250,10 +282,12 @@ print("variant ok", d, st["h_iters"], st["w_iters"])
 """
 
 
-@pytest.mark.parametrize("env", [dict(SNMFNAT_FORCE_GENERIC="1")], ids=["generic_kernels"])
+@pytest.mark.parametrize("env", [dict(SNMFNAT_FORCE_GENERIC="1"), dict(SNMFNAT_HSOLVE="ms"), dict(SNMFNAT_HSOLVE="single")],
+                         ids=["generic_kernels", "hsolve_ms_forced", "hsolve_single_forced"])
 def test_alternative_kernel_generations_agree_with_oracle(env):
     """SNMFNAT_FORCE_GENERIC=1 selects the any-geometry kernels (the ones every non-shipped rank/frame-length falls back
-    to); they must reproduce the oracle too.  The switch is read once per process."""
+    to); SNMFNAT_HSOLVE=ms / single force the multi-stream (one live stream in a 7-stream cluster) / the per-stream H-solve
+    whatever the number of active streams.  All must reproduce the oracle.  The switches are read once per process."""
     import os
     import subprocess
     import sys
