@@ -18,7 +18,7 @@ LIB = HERE / "libsnmfnat.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-DSNMFNAT_BUILD"]
+         "--expt-relaxed-constexpr", "-DSNMFNAT_BUILD"] + os.environ.get("SNMFNAT_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -18,6 +18,7 @@
 // Results per stream do not depend on which streams share a cluster.
 #include <cooperative_groups.h>
 #include <cmath>
+#include <cstdlib>
 #include "online.cuh"
 #include "online_dev.cuh"
 
@@ -36,19 +37,32 @@ constexpr int MS_KT = MS_KS / 8;        // 19 atom tiles
 constexpr int MS_HLD = 216;             // row stride of hS / gpart (== 8 mod 16: conflict-free 16-byte fragment loads)
 constexpr int MS_ROWLEN = 204;          // doubles per exchanged row: [0,152) shared atoms, [152,202) private, [202] flag / cost
 constexpr int MS_PRIV0 = 152, MS_FLAG = 202;
-constexpr unsigned MS_ROWBYTES = MS_ROWLEN * 8;
 constexpr int MS_RLD = 72;              // row stride of rS (== 8 mod 16)
 constexpr int MS_LLD = 66;              // row stride of lam_p (== 2 mod 8)
 constexpr int MS_XB = MS_RX / 8, MS_XR = MS_RX % 8;   // the x | d boundary inside atom tile XB
 static_assert(MS_XR % 2 == 0, "the two atoms of a lane's pair must belong to the same class");
 
+// Phase probe (build with -DSNMFNAT_MS_PROBE): thread 0 of rank 0 of cluster 0 accumulates clock64 deltas per phase.
+#ifdef SNMFNAT_MS_PROBE
+__device__ unsigned long long g_ms_probe[16];
+#define MS_TICK(i)                                                       \
+  do {                                                                   \
+    if (probe) {                                                         \
+      const long long t_ = clock64();                                    \
+      atomicAdd(&g_ms_probe[i], (unsigned long long)(t_ - tprev));       \
+      tprev = t_;                                                        \
+    }                                                                    \
+  } while (0)
+#else
+#define MS_TICK(i) do {} while (0)
+#endif
+
 template <int S>
 struct MsLayout {
   static constexpr size_t off_Wp = 0;                                          // [S][RA][64] swizzled private columns
-  static constexpr size_t off_hS = off_Wp + (size_t)S * MS_RA * MS_ROWS;       // [8][HLD]  h./wn per stream; aliased by gpart
+  static constexpr size_t off_hS = off_Wp + (size_t)S * MS_RA * MS_ROWS;       // [8][HLD]  h./wn per stream (+ done flag)
   static constexpr size_t off_recv = off_hS + 8 * MS_HLD;                      // [8][ROWLEN] partials of the owned stream
-  static constexpr size_t off_stage = off_recv + 8 * MS_ROWLEN;                // [ROWLEN] the owner's outgoing row
-  static constexpr size_t off_lamp = off_stage + MS_ROWLEN;                    // [8][LLD] private part of Lambda
+  static constexpr size_t off_lamp = off_recv + 8 * MS_ROWLEN;                 // [8][LLD] private part of Lambda
   static constexpr size_t off_rS = off_lamp + 8 * MS_LLD;                      // [8][RLD] ratio v./Lambda
   static constexpr size_t off_costw = off_rS + 8 * MS_RLD;                     // [9][8] cost partials per warp (+ tail row)
   static constexpr size_t off_WnS = off_costw + 72;                            // [KS] tail row of the shared columns
@@ -83,62 +97,102 @@ __global__ void ms_colstat_kernel(const double* __restrict__ Bx, const double* _
   }
 }
 
-// MODE 0: all atoms; 1: speech atoms only (B_x A_x); 2: noise atoms only (B_d A_d)
-template <int MODE>
-__device__ __forceinline__ void ms_pass_a_shared(const double (&Wa)[2 * MS_KT], const double* __restrict__ hb, int lj,
-                                                 double& c0, double& c1) {
+__device__ __forceinline__ double2 ms_lds2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+// The private atom pairs (k, k+1) are visited class by class (k & 7 = 0, 2, 4, 6) so that the swizzled column addresses of
+// a whole class are one XOR-ed base plus compile-time offsets: pair t of the schedule starts at atom ms_pk(t).
+__host__ __device__ constexpr int ms_pk(int t) {
+  return t < 7 ? 8 * t : (t < 13 ? 2 + 8 * (t - 7) : (t < 19 ? 4 + 8 * (t - 13) : 6 + 8 * (t - 19)));
+}
+static_assert(MS_RA == 50, "ms_pk covers the 25 atom pairs of R_a = 50");
+
+// Lambda pass of one warp: the 8 x 8 accumulator tile (rows 8 warp .. +7, all streams) of the shared columns on the tensor
+// cores, interleaved with the private mat-vec of stream `warp` (lanes <-> row pairs) so that the FP64 pipe and the
+// shared-memory pipe are busy together.  MODE 0: all atoms; 1: speech atoms only (B_x A_x); 2: noise atoms only (B_d A_d).
+//   hb  : shared-memory address of hS[li][2 lj]              (B fragments: atoms 8u + 2 lj + {0,1} of stream li)
+//   wX  : address of the stream's private columns + 16 lane  (row pair `lane` of atom k at (wX ^ ((k & 7) << 4)) + 512 k)
+//   hp  : address of hS[warp][PRIV0]
+template <int MODE, bool PRIV>
+__device__ __forceinline__ void ms_pass_a(const double (&Wa)[2 * MS_KT], unsigned hb, int lj, unsigned wX, unsigned hp,
+                                          double& c0, double& c1, double& l0, double& l1) {
   double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  constexpr int PSTEPS = MS_RA / 2;
 #pragma unroll
   for (int u = 0; u < MS_KT; ++u) {
-    if (MODE == 1 && (u > MS_XB || (u == MS_XB && MS_XR == 0))) continue;
-    if (MODE == 2 && u < MS_XB) continue;
-    double2 hh = *reinterpret_cast<const double2*>(hb + 8 * u);
-    if (MODE != 0 && u == MS_XB) {
-      const bool is_x = 2 * lj < MS_XR;
-      if ((MODE == 1) != is_x) hh = make_double2(0.0, 0.0);
+    const bool skip = (MODE == 1 && (u > MS_XB || (u == MS_XB && MS_XR == 0))) || (MODE == 2 && u < MS_XB);
+    if (!skip) {
+      double2 hh = ms_lds2(hb + 64u * (unsigned)u);
+      if (MODE != 0 && u == MS_XB) {
+        const bool is_x = 2 * lj < MS_XR;
+        if ((MODE == 1) != is_x) hh = make_double2(0.0, 0.0);
+      }
+      if (u & 1) {
+        dmma884(q0, q1, Wa[2 * u], hh.x);
+        dmma884(q0, q1, Wa[2 * u + 1], hh.y);
+      } else {
+        dmma884(p0, p1, Wa[2 * u], hh.x);
+        dmma884(p0, p1, Wa[2 * u + 1], hh.y);
+      }
     }
-    if (u & 1) {
-      dmma884(q0, q1, Wa[2 * u], hh.x);
-      dmma884(q0, q1, Wa[2 * u + 1], hh.y);
-    } else {
-      dmma884(p0, p1, Wa[2 * u], hh.x);
-      dmma884(p0, p1, Wa[2 * u + 1], hh.y);
+    if (PRIV) {
+#pragma unroll
+      for (int t = (u * PSTEPS) / MS_KT; t < ((u + 1) * PSTEPS) / MS_KT; ++t) {
+        const int k = ms_pk(t);
+        const double2 hh = ms_lds2(hp + 8u * (unsigned)k);
+        const double2 w0 = ms_lds2((wX ^ ((unsigned)(k & 7) << 4)) + 512u * (unsigned)k);
+        const double2 w1 = ms_lds2((wX ^ ((unsigned)((k + 1) & 7) << 4)) + 512u * (unsigned)(k + 1));
+        a0 = fma(w0.x, hh.x, a0);
+        a1 = fma(w0.y, hh.x, a1);
+        b0 = fma(w1.x, hh.y, b0);
+        b1 = fma(w1.y, hh.y, b1);
+      }
     }
   }
   c0 = p0 + q0;
   c1 = p1 + q1;
+  l0 = a0 + b0;
+  l1 = a1 + b1;
 }
 
-// private part of Lambda for stream `warp`: lanes <-> row pairs; result to lam_p[warp][2*lane .. +1]
-__device__ __forceinline__ void ms_pass_a_private(const double* __restrict__ wp, const double* __restrict__ hp, int lane,
-                                                  double* __restrict__ out) {
-  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll 5
-  for (int k = 0; k < MS_RA; k += 2) {
-    const double2 hh = *reinterpret_cast<const double2*>(hp + k);
-    const double2 w0 = *reinterpret_cast<const double2*>(wp + (size_t)k * MS_ROWS + 2 * (lane ^ (k & 7)));
-    const double2 w1 = *reinterpret_cast<const double2*>(wp + (size_t)(k + 1) * MS_ROWS + 2 * (lane ^ ((k + 1) & 7)));
-    a0 = fma(w0.x, hh.x, a0);
-    a1 = fma(w0.y, hh.x, a1);
-    b0 = fma(w1.x, hh.y, b0);
-    b1 = fma(w1.y, hh.y, b1);
-  }
-  *reinterpret_cast<double2*>(out + 2 * lane) = make_double2(a0 + b0, a1 + b1);
-}
-
-template <int NT>
-__device__ __forceinline__ void ms_pass_b_shared(const double (&Wb)[3][16], const double* __restrict__ rb,
-                                                 double (&g)[3][2]) {
+// g pass of one warp: NT atom tiles (atoms 8 (warp + 8q) .. +7, all streams) over this CTA's 64 rows on the tensor cores,
+// interleaved with the private mat-vec of stream `warp` (lanes <-> atoms lane and 32 + lane, row pairs in the order
+// p = u + 8 j so that the 4 pairs of a step share one XOR-ed base).
+//   rb : address of rS[li][2 lj]     rp : address of rS[warp][0]
+//   wx0 / wx1 : (column base of the lane's atom) ^ ((atom & 7) << 4)
+template <int NT, bool PRIV>
+__device__ __forceinline__ void ms_pass_b(const double (&Wb)[3][16], unsigned rb, unsigned rp, unsigned wx0, unsigned wx1,
+                                          double (&g)[3][2], double& ga, double& gb) {
+  double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
 #pragma unroll
   for (int q = 0; q < 3; ++q) g[q][0] = g[q][1] = 0.0;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const double2 rr = *reinterpret_cast<const double2*>(rb + 8 * u);
+    const double2 rr = ms_lds2(rb + 64u * (unsigned)u);
 #pragma unroll
     for (int q = 0; q < NT; ++q) dmma884(g[q][0], g[q][1], Wb[q][2 * u], rr.x);
 #pragma unroll
     for (int q = 0; q < NT; ++q) dmma884(g[q][0], g[q][1], Wb[q][2 * u + 1], rr.y);
+    if (PRIV) {
+      const unsigned b0 = wx0 ^ ((unsigned)u << 4), b1 = wx1 ^ ((unsigned)u << 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 r2 = ms_lds2(rp + 16u * (unsigned)(u + 8 * j));
+        const double2 w0 = ms_lds2(b0 + 128u * (unsigned)j);
+        const double2 w1 = ms_lds2(b1 + 128u * (unsigned)j);
+        x0 = fma(w0.x, r2.x, x0);
+        x1 = fma(w0.y, r2.y, x1);
+        y0 = fma(w1.x, r2.x, y0);
+        y1 = fma(w1.y, r2.y, y1);
+      }
+    }
   }
+  ga = x0 + x1;
+  gb = y0 + y1;
 }
 
 template <int S>
@@ -161,16 +215,13 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   extern __shared__ __align__(1024) double smem[];
   double* Wp = smem + L::off_Wp;
   double* hS = smem + L::off_hS;
-  double* gpart = hS;                   // same rows: a row is h./wn from the owner's send until pass B overwrites it
   double* recv = smem + L::off_recv;
-  double* stage = smem + L::off_stage;
   double* lam_p = smem + L::off_lamp;
   double* rS = smem + L::off_rS;
   double* costw = smem + L::off_costw;
   double* WnS = smem + L::off_WnS;
   double* WnP = smem + L::off_WnP;
   double* rN = smem + L::off_rN;
-  double* lamN = rN + 8;
   double* hsumw = smem + L::off_hsum;
   int* slot_s = reinterpret_cast<int*>(smem + L::off_slot);
   const unsigned barRS = (unsigned)__cvta_generic_to_shared(smem + L::off_bar);
@@ -250,9 +301,10 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     v[e] = 1.0;
     if (slot >= 0) v[e] = fmax(fr.Ym[(size_t)(st.frame_base[slot] + g_step) * LDF + f0 + 8 * warp + li], flr);  // sparse_nmf.m:169
   }
-  double vN = 1.0;        // tail row: lane n of warp 7
-  if (tail_rank && warp == MS_WARPS - 1 && lane < S && slot_s[lane] >= 0)
-    vN = fmax(fr.Ym[(size_t)(st.frame_base[slot_s[lane]] + g_step) * LDF + FT], flr);
+  // a stream's private columns (and its tail-row element) are handled by warp == stream index
+  const bool own_stream = warp < S && slot_s[warp < S ? warp : 0] >= 0;
+  double vN = 1.0;        // V of the tail row of stream `warp`
+  if (tail_rank && own_stream) vN = fmax(fr.Ym[(size_t)(st.frame_base[slot_s[warp]] + g_step) * LDF + FT], flr);
 
   // ---- small buffers ----
   for (int i = tid; i < 8 * MS_HLD; i += MS_THREADS) hS[i] = 0.0;
@@ -272,75 +324,62 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   asm volatile("cp.async.wait_all;" ::: "memory");
   cluster.sync();   // barriers initialised everywhere, local buffers staged
 
-  // ---- exchange helpers ----
+  // ---- exchange: every value is pushed by the lane that produced it (st.async; the receiver's mbarrier counts the bytes) ----
   unsigned parRS = 0, parAG = 0;
-  // every CTA sends its partial row of stream o to the owner o; the owner's barrier counts 8 rows
-  auto push_partials = [&]() {
-    hf_fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      if (rank < S) hf_mbar_expect_tx(barRS, 8u * MS_ROWBYTES);
-      hf_mbar_expect_tx(barAG, (unsigned)S * MS_ROWBYTES);
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(recv + (size_t)rank * MS_ROWLEN);
-#pragma unroll
-      for (int o = 0; o < S; ++o)
-        hf_bulk_push(hf_mapa(dst, o), (unsigned)__cvta_generic_to_shared(gpart + (size_t)o * MS_HLD), MS_ROWBYTES,
-                     hf_mapa(barRS, o));
-    }
+  const unsigned recv_mine = (unsigned)__cvta_generic_to_shared(recv + (size_t)rank * MS_ROWLEN);   // my row at an owner
+  const unsigned hS_mine = (unsigned)__cvta_generic_to_shared(hS + (size_t)rank * MS_HLD);          // my row at a peer
+  // partial of (atom index idx of the row layout, stream n) to the owner n
+  auto push_partial = [&](int n, int idx, double x) {
+    hf_st_async(hf_mapa(recv_mine + 8u * (unsigned)idx, (unsigned)n), x, hf_mapa(barRS, (unsigned)n));
   };
-  // the owner sends its staged row to row `rank` of hS in all 8 CTAs
-  auto push_row = [&]() {
-    hf_fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(hS + (size_t)rank * MS_HLD);
-      const unsigned src = (unsigned)__cvta_generic_to_shared(stage);
-#pragma unroll
-      for (int c = 0; c < MS_CL; ++c) hf_bulk_push(hf_mapa(dst, c), src, MS_ROWBYTES, hf_mapa(barAG, c));
-    }
-  };
+  constexpr unsigned RS_BYTES = 8u * (MS_KS + MS_RA + 1) * 8u;    // per round at an owner: 8 ranks x (152 + 50 atoms + cost)
+  constexpr unsigned AG_BYTES = (unsigned)S * (MS_RS + MS_RA + 1) * 8u;   // per round at every CTA: S owners x (200 atoms + flag)
 
   // ---- norms / sums of the private columns over this CTA's rows (sparse_nmf.m:157-160,192): partials to the owners ----
   const int a0 = lane, a1 = 32 + lane;
   const bool has1 = a1 < MS_RA;
-  // a stream's private columns are handled by warp == stream index
-  const bool own_stream = warp < S && slot_s[warp < S ? warp : 0] >= 0;
   const double* wp_mine = Wp + (size_t)(warp < S ? warp : 0) * MS_RA * MS_ROWS;
-  // pair p of atom a sits at byte (base(a) ^ ((a & 7) << 4)) ^ (p << 4): the column base is 512-byte aligned
+  // pair p of atom a sits at byte (base(a) ^ ((a & 7) << 4)) ^ (p << 4): the column base is 512-byte aligned.  Lanes without a
+  // second atom read the first one again (no predicated loads); their result is never pushed.
+  const int a1c = has1 ? a1 : a0;
   const unsigned wx0 = ((unsigned)__cvta_generic_to_shared(wp_mine + (size_t)a0 * MS_ROWS)) ^ ((unsigned)(a0 & 7) << 4);
-  const unsigned wx1 = ((unsigned)__cvta_generic_to_shared(wp_mine + (size_t)(has1 ? a1 : 0) * MS_ROWS)) ^ ((unsigned)((has1 ? a1 : 0) & 7) << 4);
-  if (own_stream) {
+  const unsigned wx1 = ((unsigned)__cvta_generic_to_shared(wp_mine + (size_t)a1c * MS_ROWS)) ^ ((unsigned)(a1c & 7) << 4);
+  if (tid == 0) {
+    if (rank < S) hf_mbar_expect_tx(barRS, 8u * 2u * MS_RA * 8u);
+    hf_mbar_expect_tx(barAG, AG_BYTES);
+  }
+  if (warp < S) {
     double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;
+    if (own_stream) {
 #pragma unroll 8
-    for (int p = 0; p < 32; ++p) {
-      double2 w0, w1 = make_double2(0.0, 0.0);
-      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w0.x), "=d"(w0.y) : "r"(wx0 ^ ((unsigned)p << 4)));
-      if (has1) asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w1.x), "=d"(w1.y) : "r"(wx1 ^ ((unsigned)p << 4)));
-      s1a += w0.x + w0.y;
-      s2a = fma(w0.x, w0.x, fma(w0.y, w0.y, s2a));
-      s1b += w1.x + w1.y;
-      s2b = fma(w1.x, w1.x, fma(w1.y, w1.y, s2b));
+      for (int p = 0; p < 32; ++p) {
+        const double2 w0 = ms_lds2(wx0 ^ ((unsigned)p << 4)), w1 = ms_lds2(wx1 ^ ((unsigned)p << 4));
+        s1a += w0.x + w0.y;
+        s2a = fma(w0.x, w0.x, fma(w0.y, w0.y, s2a));
+        s1b += w1.x + w1.y;
+        s2b = fma(w1.x, w1.x, fma(w1.y, w1.y, s2b));
+      }
+      if (tail_rank) {
+        const double t0 = WnP[warp * MS_RA + a0], t1 = WnP[warp * MS_RA + a1c];
+        s1a += t0;
+        s2a = fma(t0, t0, s2a);
+        s1b += t1;
+        s2b = fma(t1, t1, s2b);
+      }
     }
-    if (tail_rank) {
-      const double t0 = WnP[warp * MS_RA + a0], t1 = has1 ? WnP[warp * MS_RA + a1] : 0.0;
-      s1a += t0;
-      s2a = fma(t0, t0, s2a);
-      s1b += t1;
-      s2b = fma(t1, t1, s2b);
-    }
-    double* row = gpart + (size_t)warp * MS_HLD;
-    row[a0] = s1a;
-    row[MS_PRIV0 + a0] = s2a;
+    push_partial(warp, a0, s1a);
+    push_partial(warp, MS_PRIV0 + a0, s2a);
     if (has1) {
-      row[a1] = s1b;
-      row[MS_PRIV0 + a1] = s2b;
+      push_partial(warp, a1, s1b);
+      push_partial(warp, MS_PRIV0 + a1, s2b);
     }
   }
-  push_partials();
 
-  // ---- owner state: thread a < 200 <-> atom a of the row layout (shared atoms first) ----
-  // (threads 200..203 fill the two pad atoms, the done flag and the spare slot of the outgoing row)
+  // ---- owner state: thread a < 200 <-> atom a of the row layout (shared atoms first); thread 202 carries the done flag.
+  //      Only warps 0..6 take part: each of them pushes after its reads of recv, so a peer can never overwrite a value that
+  //      is still to be read ----
   const bool is_atom = tid < MS_RS + MS_RA;
+  const bool owner_thread = tid < 7 * 32;
   const int ridx = tid < MS_RS ? tid : tid + (MS_PRIV0 - MS_RS);
   // position of the atom in the reference's H: [x | adapted d | fixed d]
   const int orig = tid < MS_RX ? tid : (tid < MS_RS ? tid + MS_RA : tid - MS_RF);
@@ -348,14 +387,16 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   int it = 0;
   bool done = my_slot < 0;
   double last_cost = INFINITY, cost = 0.0;
-  auto stage_row = [&](double x) {
-    if (is_atom) stage[ridx] = x;
-    else if (tid < MS_ROWLEN) {
-      const int idx = tid == 200 ? MS_RS : (tid == 201 ? MS_RS + 1 : tid);
-      stage[idx] = (idx == MS_FLAG && done) ? 1.0 : 0.0;
+  // the owner's row (x for the atoms, the done flag) to all 8 CTAs
+  auto push_row = [&](double x) {
+    if (is_atom || tid == MS_FLAG) {
+      const double val = is_atom ? x : (done ? 1.0 : 0.0);
+      const unsigned off = 8u * (unsigned)(is_atom ? ridx : MS_FLAG);
+#pragma unroll
+      for (int c = 0; c < MS_CL; ++c) hf_st_async(hf_mapa(hS_mine + off, (unsigned)c), val, hf_mapa(barAG, (unsigned)c));
     }
   };
-  if (rank < S) {
+  if (rank < S && owner_thread) {
     hf_mbar_wait_bounded(barRS, parRS);
     parRS ^= 1u;
     if (is_atom && my_slot >= 0) {
@@ -377,37 +418,51 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
       dph = 1.0 / fmax(s1 / wn + sc.sparsity, flr);   // reciprocal of the H-update denominator, sparse_nmf.m:192-193
       h = h_init[orig] * wn;                          // :160
     }
-    double hs = warp_sum(h);
+    const double hs = warp_sum(h);
     if (lane == 0) hsumw[warp] = hs;
-    stage_row(h * inv_wn);
-    push_row();
+    push_row(h * inv_wn);
   }
 
   // ---- multiplicative updates ----
-  const double* hb = hS + (size_t)li * MS_HLD + 2 * lj;   // B fragments of the Lambda pass
-  const double* rb = rS + (size_t)li * MS_RLD + 2 * lj;   // B fragments of the g pass
+  const unsigned hb = (unsigned)__cvta_generic_to_shared(hS + (size_t)li * MS_HLD + 2 * lj);   // B fragments of the Lambda pass
+  const unsigned rb = (unsigned)__cvta_generic_to_shared(rS + (size_t)li * MS_RLD + 2 * lj);   // B fragments of the g pass
+  const unsigned hp_mine = (unsigned)__cvta_generic_to_shared(hS + (size_t)(warp < S ? warp : 0) * MS_HLD + MS_PRIV0);
+  const unsigned rp_mine = (unsigned)__cvta_generic_to_shared(rS + (size_t)(warp < S ? warp : 0) * MS_RLD);
+  const unsigned wX = (unsigned)__cvta_generic_to_shared(wp_mine) + 16u * (unsigned)lane;
+  double* lamp_mine = lam_p + (size_t)(warp < S ? warp : 0) * MS_LLD;
   const int frow = 8 * warp + li;
 
-  // tail row (row 512) on the last rank, warp 7: lanes <-> atoms, one stream after the other
-  auto tail_lambda = [&](int mode) {
+  // tail row (row 512, last rank): Lambda of stream `warp`, lanes <-> atom pairs.  mode as in ms_pass_a
+  auto tail_lambda = [&](int mode) -> double {
+    double s = 0.0;
+    const double* hr = hS + (size_t)warp * MS_HLD;
 #pragma unroll
-    for (int n = 0; n < S; ++n) {
-      double s = 0.0;
-      const double* hr = hS + (size_t)n * MS_HLD;
-      for (int a = lane; a < MS_KS; a += 32) {
+    for (int j = 0; j < 3; ++j) {
+      const int a = 2 * (lane + 32 * j);
+      if (a < MS_KS) {
         const bool is_x = a < MS_RX;
-        if (mode == 0 || (mode == 1) == is_x) s = fma(WnS[a], hr[a], s);
+        if (mode == 0 || (mode == 1) == is_x) {
+          const double2 w = *reinterpret_cast<const double2*>(WnS + a);
+          const double2 x = *reinterpret_cast<const double2*>(hr + a);
+          s = fma(w.x, x.x, fma(w.y, x.y, s));
+        }
       }
-      if (mode != 1)
-        for (int a = lane; a < MS_RA; a += 32) s = fma(WnP[n * MS_RA + a], hr[MS_PRIV0 + a], s);
-      s = warp_sum(s);
-      if (lane == 0) lamN[n] = s;
     }
-    __syncwarp();
+    if (mode != 1 && 2 * lane < MS_RA) {
+      const double2 w = *reinterpret_cast<const double2*>(WnP + warp * MS_RA + 2 * lane);
+      const double2 x = *reinterpret_cast<const double2*>(hr + MS_PRIV0 + 2 * lane);
+      s = fma(w.x, x.x, fma(w.y, x.y, s));
+    }
+    return warp_sum(s);
   };
 
+#ifdef SNMFNAT_MS_PROBE
+  const bool probe = blockIdx.x == 0 && tid == 0;
+  long long tprev = clock64();
+#endif
   for (;;) {
     hf_mbar_wait_bounded(barAG, parAG);
+    MS_TICK(0);
     parAG ^= 1u;
     bool all_done = true, mine_done = true;
 #pragma unroll
@@ -417,23 +472,36 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
       if (n == warp) mine_done = dn;
     }
     if (all_done) break;
+    if (tid == 0) {   // this round's exchanges
+      if (rank < S) hf_mbar_expect_tx(barRS, RS_BYTES);
+      hf_mbar_expect_tx(barAG, AG_BYTES);
+    }
+    const bool priv = own_stream && !mine_done;
     // (A) Lambda = W h: shared columns on the tensor cores, private columns as a mat-vec
     double c0, c1;
-    ms_pass_a_shared<0>(Wa, hb, lj, c0, c1);
-    if (own_stream && !mine_done) ms_pass_a_private(wp_mine, hS + (size_t)warp * MS_HLD + MS_PRIV0, lane, lam_p + (size_t)warp * MS_LLD);
-    if (tail_rank && warp == MS_WARPS - 1) {
-      tail_lambda(0);
-      double ctn = 0.0;
-      if (lane < S) {
-        const double lam = fmax(lamN[lane], flr);
-        const double r = vN * fast_rcp(lam);
-        const bool live = slot_s[lane] >= 0;
-        rN[lane] = live ? r : 0.0;
-        ctn = live ? fma(vN, fast_log(r, log_tab), lam - vN) : 0.0;
-      }
-      if (lane < 8) costw[64 + lane] = ctn;
+    if (priv) {
+      double l0, l1;
+      ms_pass_a<0, true>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      *reinterpret_cast<double2*>(lamp_mine + 2 * lane) = make_double2(l0, l1);
+    } else {
+      double l0, l1;
+      ms_pass_a<0, false>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
     }
+    if (tail_rank && warp < S) {
+      double ctn = 0.0, rn = 0.0;
+      if (priv) {
+        const double lam = fmax(tail_lambda(0), flr);
+        rn = vN * fast_rcp(lam);
+        ctn = fma(vN, fast_log(rn, log_tab), lam - vN);
+      }
+      if (lane == 0) {
+        rN[warp] = rn;
+        costw[64 + warp] = ctn;
+      }
+    }
+    MS_TICK(1);
     __syncthreads();
+    MS_TICK(2);
     // (R) ratio and KL terms on the accumulator fragments
     {
       double ct[2];
@@ -457,55 +525,53 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
       }
     }
     __syncthreads();
-    // (B) g = W' r: partial over this CTA's rows
+    MS_TICK(3);
+    // (B) g = W' r: partial over this CTA's rows, pushed to the owners straight from the registers
     {
-      double g[3][2];
-      if (warp < MS_KT - 16) ms_pass_b_shared<3>(Wb, rb, g); else ms_pass_b_shared<2>(Wb, rb, g);
+      double g[3][2], ga, gb;
+      const bool nt3 = warp < MS_KT - 16;
+      if (nt3) {
+        if (priv) ms_pass_b<3, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb); else ms_pass_b<3, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb);
+      } else {
+        if (priv) ms_pass_b<2, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb); else ms_pass_b<2, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb);
+      }
+      // the lane's two streams are n = 2 lj and 2 lj + 1: remote addresses of its first atom in their owners' rows
+      const unsigned la = recv_mine + 8u * (unsigned)(8 * warp + li);
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        if (warp + 8 * q >= MS_KT) break;
-        const int a = 8 * (warp + 8 * q) + li;
+      for (int e = 0; e < 2; ++e) {
+        const int n = 2 * lj + e;
+        if (n < S) {
+          const unsigned ra = hf_mapa(la, (unsigned)n), rbar = hf_mapa(barRS, (unsigned)n);
+          const double rn = tail_rank ? rN[n] : 0.0;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          double x = g[q][e];
-          if (tail_rank) x = fma(WnS[a], rN[2 * lj + e], x);
-          gpart[(size_t)(2 * lj + e) * MS_HLD + a] = x;
+          for (int q = 0; q < 3; ++q) {
+            if (q == 2 && !nt3) break;
+            double x = g[q][e];
+            if (tail_rank) x = fma(WnS[8 * (warp + 8 * q) + li], rn, x);
+            hf_st_async(ra + 512u * (unsigned)q, x, rbar);
+          }
         }
       }
-    }
-    if (own_stream && !mine_done) {
-      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
-      const double2* rp = reinterpret_cast<const double2*>(rS + (size_t)warp * MS_RLD);
-#pragma unroll 8
-      for (int p = 0; p < 32; ++p) {
-        const double2 rr = rp[p];
-        double2 w0, w1 = make_double2(0.0, 0.0);
-        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w0.x), "=d"(w0.y) : "r"(wx0 ^ ((unsigned)p << 4)));
-        if (has1) asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w1.x), "=d"(w1.y) : "r"(wx1 ^ ((unsigned)p << 4)));
-        x0 = fma(w0.x, rr.x, x0);
-        x1 = fma(w0.y, rr.y, x1);
-        y0 = fma(w1.x, rr.x, y0);
-        y1 = fma(w1.y, rr.y, y1);
+      if (warp < S) {
+        if (tail_rank) {
+          ga = fma(WnP[warp * MS_RA + a0], rN[warp], ga);
+          gb = fma(WnP[warp * MS_RA + a1c], rN[warp], gb);
+        }
+        push_partial(warp, MS_PRIV0 + a0, ga);
+        if (has1) push_partial(warp, MS_PRIV0 + a1, gb);
       }
-      double ga = x0 + x1, gb = y0 + y1;
-      if (tail_rank) {
-        ga = fma(WnP[warp * MS_RA + a0], rN[warp], ga);
-        if (has1) gb = fma(WnP[warp * MS_RA + a1], rN[warp], gb);
-      }
-      double* row = gpart + (size_t)warp * MS_HLD + MS_PRIV0;
-      row[a0] = ga;
-      if (has1) row[a1] = gb;
-    }
-    if (warp == MS_WARPS - 1 && lane < S) {
-      double s = 0.0;
+      if (warp == MS_WARPS - 1 && lane < S) {
+        double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < 9; ++w) s += costw[w * 8 + lane];
-      gpart[(size_t)lane * MS_HLD + MS_FLAG] = s;
+        for (int w = 0; w < 9; ++w) s += costw[w * 8 + lane];
+        push_partial(lane, MS_FLAG, s);
+      }
     }
-    push_partials();
+    MS_TICK(4);
     // (C) owner: combine the 8 partials in rank order, stop rule, h update, send h ./ wn back
-    if (rank < S) {
+    if (rank < S && owner_thread) {
       hf_mbar_wait_bounded(barRS, parRS);
+      MS_TICK(5);
       parRS ^= 1u;
       if (!done) {
         double gk = 0.0;
@@ -519,7 +585,7 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
 #pragma unroll
           for (int c = 0; c < MS_CL; ++c) div += recv[(size_t)c * MS_ROWLEN + MS_FLAG];
 #pragma unroll
-          for (int w = 0; w < MS_WARPS; ++w) hs += hsumw[(it & 1) * 8 + w];
+          for (int w = 0; w < 7; ++w) hs += hsumw[(it & 1) * 8 + w];
           cost = div + sc.sparsity * hs;                                   // sparse_nmf.m:261
           if (it > 1 && sc.conv_eps > 0.0) {
             const double e = fabs(cost - last_cost) / last_cost;           // :274
@@ -537,15 +603,20 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
           if (lane == 0) hsumw[(it & 1) * 8 + warp] = hs;
         }
       }
-      stage_row(h * inv_wn);
-      push_row();
+      push_row(h * inv_wn);
+      MS_TICK(6);
+#ifdef SNMFNAT_MS_PROBE
+      if (probe) atomicAdd(&g_ms_probe[8], 1ull);
+#endif
     }
   }
 
   // ---- outputs of the owned stream; activations for the un-normalised basis go back out for the reconstructions ----
-  cluster.sync();   // every copy of the last round has landed: the staging rows may be rewritten
-  if (tid == 0) hf_mbar_expect_tx(barAG, (unsigned)S * MS_ROWBYTES);
-  if (rank < S) {
+  // (inside the loop an owner can only send after every CTA has passed its previous wait; here nothing orders the
+  // rounds, so a cluster barrier keeps the bytes of this round out of a peer's previous phase)
+  cluster.sync();
+  if (tid == 0) hf_mbar_expect_tx(barAG, AG_BYTES);
+  if (rank < S && owner_thread) {
     if (my_slot >= 0) {
       if (is_atom) st.A[(size_t)my_slot * R + orig] = h;
       if (tid == 0) {
@@ -553,34 +624,36 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
         st.h_cost[my_slot] = cost;
       }
     }
-    stage_row(h);
-    push_row();
+    push_row(h);
   }
   hf_mbar_wait_bounded(barAG, parAG);
   parAG ^= 1u;
   // X_hat = B_x A_x
   {
-    double c0, c1;
-    ms_pass_a_shared<1>(Wa, hb, lj, c0, c1);
+    double c0, c1, l0, l1;
+    ms_pass_a<1, false>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int n = 2 * lj + e;
       if (n < S && slot_s[n] >= 0) st.Xhat[(size_t)slot_s[n] * LDF + f0 + frow] = e ? c1 : c0;
     }
-    if (tail_rank && warp == MS_WARPS - 1) {
-      tail_lambda(1);
-      if (lane < S && slot_s[lane] >= 0) st.Xhat[(size_t)slot_s[lane] * LDF + FT] = lamN[lane];
-      __syncwarp();
+    if (tail_rank && own_stream) {
+      const double x = tail_lambda(1);
+      if (lane == 0) st.Xhat[(size_t)slot_s[warp] * LDF + FT] = x;
     }
   }
   // D_hat = B_d A_d
   {
-    double c0, c1;
-    ms_pass_a_shared<2>(Wa, hb, lj, c0, c1);
-    if (own_stream) ms_pass_a_private(wp_mine, hS + (size_t)warp * MS_HLD + MS_PRIV0, lane, lam_p + (size_t)warp * MS_LLD);
-    if (tail_rank && warp == MS_WARPS - 1) {
-      tail_lambda(2);
-      if (lane < S && slot_s[lane] >= 0) st.Dhat[(size_t)slot_s[lane] * LDF + FT] = lamN[lane];
+    double c0, c1, l0, l1;
+    if (own_stream) {
+      ms_pass_a<2, true>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      *reinterpret_cast<double2*>(lamp_mine + 2 * lane) = make_double2(l0, l1);
+    } else {
+      ms_pass_a<2, false>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+    }
+    if (tail_rank && own_stream) {
+      const double x = tail_lambda(2);
+      if (lane == 0) st.Dhat[(size_t)slot_s[warp] * LDF + FT] = x;
     }
     __syncthreads();
 #pragma unroll
@@ -590,7 +663,7 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
         st.Dhat[(size_t)slot_s[n] * LDF + f0 + frow] = (e ? c1 : c0) + lam_p[(size_t)n * MS_LLD + frow];
     }
   }
-  cluster.sync();  // nobody may exit while a peer's bulk copy can still target its shared memory
+  cluster.sync();  // nobody may exit while a peer can still push into its shared memory
 }
 
 // ---- host side ----
@@ -618,10 +691,38 @@ void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars
   const size_t bytes = MsLayout<MS_S>::bytes;
   SN_CUDA(cudaFuncSetAttribute(hsolve_ms_kernel<MS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const int groups = (n_active + MS_S - 1) / MS_S;
+  static bool reported = false;
+  if (!reported && getenv("SNMFNAT_DEBUG")) {
+    reported = true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(MS_CL * groups);
+    cfg.blockDim = dim3(MS_THREADS);
+    cfg.dynamicSmemBytes = bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = MS_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, hsolve_ms_kernel<MS_S>, &cfg);
+    fprintf(stderr, "snmfnat: hsolve_ms_kernel<%d>: %zu bytes of shared memory, max active clusters = %d (%s)\n", MS_S, bytes, nc,
+            cudaGetErrorString(e));
+  }
   hsolve_ms_kernel<MS_S><<<dim3(MS_CL * groups), dim3(MS_THREADS), bytes, ctx->stream>>>(
       d, sc, st, fr, h_init, g_step, log_table(ctx), st.ms_colstat, st.ms_perm, n_active);
   count_launch(ctx);
   check_launch(ctx, "hsolve_ms_kernel");
+#ifdef SNMFNAT_MS_PROBE
+  static int nl = 0;
+  if (++nl == 100) {
+    SN_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long pr[16];
+    SN_CUDA(cudaMemcpyFromSymbol(pr, g_ms_probe, sizeof(pr)));
+    const double it = (double)(pr[8] ? pr[8] : 1);
+    fprintf(stderr, "snmfnat ms probe (clk per iteration over %.0f iterations): waitAG %.0f | passA %.0f | bar1 %.0f | ratio+bar2 %.0f | "
+            "passB+push %.0f | waitRS %.0f | owner+pushrow %.0f\n", it, pr[0] / it, pr[1] / it, pr[2] / it, pr[3] / it, pr[4] / it,
+            pr[5] / it, pr[6] / it);
+  }
+#endif
 }
 
 }  // namespace snmfnat
