@@ -336,7 +336,8 @@ int snmfnat_batch_run(snmfnat_batch* b) {
       if (!mel) {
         launch_hsolve(ctx, dq, c.sc, st, fr, b->sb.h_init.p, nq, g);
         mark();
-        launch_gain(ctx, dq, c.sc, st, fr, trp, nq, g);
+        const int na_next = g + 1 < b->max_hops ? b->active_at[g + 1] : 0;
+        launch_gain(ctx, dq, c.sc, st, fr, trp, nq, g, na_next > q ? (na_next - q + NG - 1) / NG : 0);
         mark();
         launch_wsolve(ctx, dq, c.sc, st, trp, nq, g);
         mark();

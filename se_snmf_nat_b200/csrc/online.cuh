@@ -69,7 +69,12 @@ struct SlotState {
   unsigned long long* stats;    // [8]: hops, h_iters, w_iters, gated, w_solves, w_atoms
   // multi-stream H-solve (online_ms.cu): norms / sums of the stream-invariant columns, optional launch order of the slots
   const double* ms_colstat = nullptr;
-  const int* ms_perm = nullptr;
+  // launch order of the next hop, written by the last CTA of gain_kernel: positions of the group's slots sorted by the
+  // iteration count of this hop, longest first ([16][ms_perm_stride]); ms_perm_step[group] = the step it is valid for
+  int* ms_perm = nullptr;
+  int* ms_perm_step = nullptr;
+  int* ms_ticket = nullptr;
+  int ms_perm_stride = 0;
 };
 
 // Per-frame arrays shared by the STFT, the solvers and the ISTFT.
@@ -91,8 +96,9 @@ struct TraceArrays {
 void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const FrameArrays& fr, const double* h_init, int n_active, int g_step);
 // blk_sparse + gain + adaptation gate/history for slots [0, n_active).
+// n_active_next >= 0: also sort the slots of the launch for the next hop's multi-stream H-solve (see SlotState::ms_perm)
 void launch_gain(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
-                 const FrameArrays& fr, const TraceArrays* tr, int n_active, int g_step);
+                 const FrameArrays& fr, const TraceArrays* tr, int n_active, int g_step, int n_active_next = -1);
 // W-solve (noise-basis adaptation) for the slots whose do_update flag is set.
 void launch_wsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const TraceArrays* tr, int n_active, int g_step);

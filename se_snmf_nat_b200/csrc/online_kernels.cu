@@ -321,11 +321,52 @@ void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& s
 // =====================================================================================================
 constexpr int GN_THREADS = 256;
 
+// The last CTA of a gain launch orders the launch's slots for the next hop's multi-stream H-solve: counting sort by this
+// hop's iteration count, longest first (consecutive hops are strongly correlated, so streams that share a cluster stop
+// at about the same time and the longest solves start first); slots that are inactive at the next hop go last.
+__device__ void gain_order_next(const OnlineDims& d, const SlotState& st, int g_step, int n_next) {
+  __shared__ int hist[256], base[256];
+  __shared__ int last;
+  const int tid = threadIdx.x, n = (int)gridDim.x, grp = d.slot0 & 15;
+  __syncthreads();   // this CTA's h_iters / state writes are done
+  if (tid == 0) {
+    __threadfence();
+    last = atomicAdd(&st.ms_ticket[grp], 1) == n - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int k = tid; k < 256; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  auto key_of = [&](int i) {
+    if (i >= n_next) return 0;
+    const int it = st.h_iters[d.slot0 + i * d.slot_stride];
+    return 1 + (it < 0 ? 0 : (it > 254 ? 254 : it));
+  };
+  for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[key_of(i)], 1);
+  __syncthreads();
+  for (int k = tid; k < 256; k += blockDim.x) {
+    int b = 0;
+    for (int j = k + 1; j < 256; ++j) b += hist[j];
+    base[k] = b;
+  }
+  __syncthreads();
+  int* perm = st.ms_perm + (size_t)grp * st.ms_perm_stride;
+  for (int i = tid; i < n; i += blockDim.x) perm[atomicAdd(&base[key_of(i)], 1)] = i;
+  if (tid == 0) {
+    st.ms_ticket[grp] = 0;
+    st.ms_perm_step[grp] = g_step + 1;
+  }
+}
+
 __global__ void __launch_bounds__(GN_THREADS)
-gain_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, TraceArrays tr, int has_trace, int g_step) {
+gain_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, TraceArrays tr, int has_trace, int g_step, int n_next) {
   const int slot = d.slot0 + (int)blockIdx.x * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
-  if (l < 1 || l > st.n_hops[slot]) return;
+  if (l < 1 || l > st.n_hops[slot]) {
+    if (n_next >= 0) gain_order_next(d, st, g_step, n_next);
+    return;
+  }
   const int tid = threadIdx.x;
   const int F = d.F, LDF = d.LDF, R = d.R, R_x = d.R_x, R_d = d.R_d, R_a = d.R_a, m_a = d.m_a, PL = d.P_len_l;
   const double flr = sc.flr;
@@ -485,12 +526,13 @@ gain_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, TraceA
       tr.info[frame * 4 + 3] = 0;
     }
   }
+  if (n_next >= 0) gain_order_next(d, st, g_step, n_next);
 }
 
 static size_t gain_smem_bytes(const OnlineDims& d) { return ((size_t)5 * d.F + 64) * sizeof(double) + (size_t)d.R_a * sizeof(int) + 16; }
 
 void launch_gain(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
-                 const FrameArrays& fr, const TraceArrays* tr, int n_active, int g_step) {
+                 const FrameArrays& fr, const TraceArrays* tr, int n_active, int g_step, int n_active_next) {
   if (n_active <= 0) return;
   const size_t smem = gain_smem_bytes(d);
   SN_REQUIRE(sc.P_len_k + sc.DCbin <= d.F && sc.P_len_k >= 2, SNMFNAT_EINVAL, "P_len_k=%d does not fit F=%d", sc.P_len_k, d.F);
@@ -498,7 +540,8 @@ void launch_gain(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc,
   if (smem > 48 * 1024) SN_CUDA(cudaFuncSetAttribute(gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TraceArrays t{};
   if (tr) t = *tr;
-  gain_kernel<<<dim3(n_active), dim3(GN_THREADS), smem, ctx->stream>>>(d, sc, st, fr, t, tr ? 1 : 0, g_step);
+  const int n_next = (st.ms_perm && st.ms_perm_step && st.ms_ticket && d.slot0 < 16 && n_active <= st.ms_perm_stride) ? n_active_next : -1;
+  gain_kernel<<<dim3(n_active), dim3(GN_THREADS), smem, ctx->stream>>>(d, sc, st, fr, t, tr ? 1 : 0, g_step, n_next);
   count_launch(ctx);
   check_launch(ctx, "gain_kernel");
 }

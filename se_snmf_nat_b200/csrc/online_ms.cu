@@ -164,10 +164,23 @@ __device__ __forceinline__ void ms_pass_a(const double (&Wa)[2 * MS_KT], unsigne
 // p = u + 8 j so that the 4 pairs of a step share one XOR-ed base).
 //   rb : address of rS[li][2 lj]     rp : address of rS[warp][0]
 //   wx0 / wx1 : (column base of the lane's atom) ^ ((atom & 7) << 4)
+//   ct0 / ct1 : the lane's two KL terms v log(v / Lambda) - v + Lambda of the ratio step (sparse_nmf.m:250); they are evaluated
+//   here, off the critical path, and summed over the 8 rows of the warp's tile into costw_w[stream]
 template <int NT, bool PRIV>
 __device__ __forceinline__ void ms_pass_b(const double (&Wb)[3][16], unsigned rb, unsigned rp, unsigned wx0, unsigned wx1,
-                                          double (&g)[3][2], double& ga, double& gb) {
+                                          double (&g)[3][2], double& ga, double& gb, const double (&v)[2], const double (&lam)[2],
+                                          const double (&rat)[2], const double2* __restrict__ log_tab, double* __restrict__ costw_w,
+                                          int li, int lj) {
   double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    // rat == 0 marks a stream slot without a live stream
+    double s = rat[e] > 0.0 ? fma(v[e], fast_log(rat[e], log_tab), lam[e] - v[e]) : 0.0;
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    if (li == 0) costw_w[2 * lj + e] = s;
+  }
 #pragma unroll
   for (int q = 0; q < 3; ++q) g[q][0] = g[q][1] = 0.0;
 #pragma unroll
@@ -198,8 +211,7 @@ __device__ __forceinline__ void ms_pass_b(const double (&Wb)[3][16], unsigned rb
 template <int S>
 __global__ void __cluster_dims__(MS_CL, 1, 1) __launch_bounds__(MS_THREADS, 1)
 hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, const double* __restrict__ h_init, int g_step,
-                 const double2* __restrict__ log_tab, const double* __restrict__ colstat, const int* __restrict__ perm,
-                 int n_active) {
+                 const double2* __restrict__ log_tab, const double* __restrict__ colstat, int n_active) {
   using L = MsLayout<S>;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -232,7 +244,10 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     int slot = -1;
     const int p = grp * S + tid;
     if (tid < S && p < n_active) {
-      const int idx = perm ? perm[p] : p;
+      // launch order written by the previous hop's gain kernel (longest solve first, similar lengths together), if any
+      const int pg = d.slot0 & 15;
+      const bool sorted = st.ms_perm && d.slot0 < 16 && st.ms_perm_step[pg] == g_step;
+      const int idx = sorted ? st.ms_perm[(size_t)pg * st.ms_perm_stride + p] : p;
       slot = d.slot0 + idx * d.slot_stride;
       const int l = g_step + 1 - st.l_offset[slot];
       if (l < 1 || l > st.n_hops[slot]) slot = -1;
@@ -503,26 +518,14 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     __syncthreads();
     MS_TICK(2);
     // (R) ratio and KL terms on the accumulator fragments
-    {
-      double ct[2];
+    double lamv[2], ratv[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int n = 2 * lj + e;
-        const bool live = n < S && slot_s[n] >= 0;
-        double lam = (e ? c1 : c0) + lam_p[(size_t)n * MS_LLD + frow];
-        lam = fmax(lam, flr);
-        const double r = v[e] * fast_rcp(lam);
-        rS[(size_t)n * MS_RLD + frow] = live ? r : 0.0;
-        ct[e] = live ? fma(v[e], fast_log(r, log_tab), lam - v[e]) : 0.0;   // sparse_nmf.m:250
-      }
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        double s = ct[e];
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        if (li == 0) costw[warp * 8 + 2 * lj + e] = s;
-      }
+    for (int e = 0; e < 2; ++e) {
+      const int n = 2 * lj + e;
+      const bool live = n < S && slot_s[n] >= 0;
+      lamv[e] = fmax((e ? c1 : c0) + lam_p[(size_t)n * MS_LLD + frow], flr);
+      ratv[e] = live ? v[e] * fast_rcp(lamv[e]) : 0.0;
+      rS[(size_t)n * MS_RLD + frow] = ratv[e];
     }
     __syncthreads();
     MS_TICK(3);
@@ -531,10 +534,14 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
       double g[3][2], ga, gb;
       const bool nt3 = warp < MS_KT - 16;
       if (nt3) {
-        if (priv) ms_pass_b<3, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb); else ms_pass_b<3, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb);
+        if (priv) ms_pass_b<3, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
+        else ms_pass_b<3, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
       } else {
-        if (priv) ms_pass_b<2, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb); else ms_pass_b<2, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb);
+        if (priv) ms_pass_b<2, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
+        else ms_pass_b<2, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
       }
+      // the cost partials of all warps are summed by warp 7: the others only arrive at named barrier 1 (non-blocking)
+      if (warp != MS_WARPS - 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
       // the lane's two streams are n = 2 lj and 2 lj + 1: remote addresses of its first atom in their owners' rows
       const unsigned la = recv_mine + 8u * (unsigned)(8 * warp + li);
 #pragma unroll
@@ -560,11 +567,14 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
         push_partial(warp, MS_PRIV0 + a0, ga);
         if (has1) push_partial(warp, MS_PRIV0 + a1, gb);
       }
-      if (warp == MS_WARPS - 1 && lane < S) {
-        double s = 0.0;
+      if (warp == MS_WARPS - 1) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (lane < S) {
+          double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < 9; ++w) s += costw[w * 8 + lane];
-        push_partial(lane, MS_FLAG, s);
+          for (int w = 0; w < 9; ++w) s += costw[w * 8 + lane];
+          push_partial(lane, MS_FLAG, s);
+        }
       }
     }
     MS_TICK(4);
@@ -708,7 +718,7 @@ void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars
             cudaGetErrorString(e));
   }
   hsolve_ms_kernel<MS_S><<<dim3(MS_CL * groups), dim3(MS_THREADS), bytes, ctx->stream>>>(
-      d, sc, st, fr, h_init, g_step, log_table(ctx), st.ms_colstat, st.ms_perm, n_active);
+      d, sc, st, fr, h_init, g_step, log_table(ctx), st.ms_colstat, n_active);
   count_launch(ctx);
   check_launch(ctx, "hsolve_ms_kernel");
 #ifdef SNMFNAT_MS_PROBE

@@ -90,6 +90,9 @@ void SlotBuffers::set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B
   upload_basis(ctx, B_d, d.F, d.R_d, d.LDF, Bd_fix.p);
   if (hsolve_ms_supported(ctx, d)) {
     ms_colstat.alloc(2 * 152);
+    ms_perm.alloc((size_t)16 * S);
+    ms_perm_step.alloc(16);
+    ms_ticket.alloc(16);
     launch_ms_colstat(ctx, d, Bx.p, Bd_fix.p, ms_colstat.p);
     SN_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -211,6 +214,10 @@ void SlotBuffers::reset(snmfnat_ctx* ctx) {
   A.zero(st); Xhat.zero(st); Dhat.zero(st); Q.zero(st); G.zero(st); h_cost.zero(st);
   rblk_pos.zero(st); bd_sel.zero(st); ring_head.zero(st); h_iters.zero(st); gated.zero(st); do_update.zero(st); n_up.zero(st);
   w_iters.zero(st); err_flag.zero(st); idx_up.zero(st); idx_rem.zero(st); stats.zero(st);
+  if (ms_perm.n) {
+    ms_ticket.zero(st);
+    SN_CUDA(cudaMemsetAsync(ms_perm_step.p, 0xff, 16 * sizeof(int), st));   // -1: no order computed yet
+  }
   fill_int_kernel<<<(S + 255) / 256, 256, 0, st>>>(update_switch.p, S, 1);  // init_buff.m:41
   count_launch(ctx);
   const size_t per = (size_t)d.R_d * d.LDF;
@@ -251,6 +258,7 @@ SlotState SlotBuffers::view() const {
   v.l_offset = l_offset.p; v.n_hops = n_hops.p; v.frame_base = frame_base.p;
   v.stats = stats.p;
   v.ms_colstat = ms_colstat.p;
+  v.ms_perm = ms_perm.p; v.ms_perm_step = ms_perm_step.p; v.ms_ticket = ms_ticket.p; v.ms_perm_stride = S;
   return v;
 }
 
