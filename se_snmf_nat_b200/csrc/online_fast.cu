@@ -526,6 +526,21 @@ __device__ __forceinline__ double rows8_sum_f(double v) {
   return v;
 }
 
+// Phase probe (build with -DSNMFNAT_WS_PROBE): thread 0 of the first updating cluster's rank 0 accumulates clock64 deltas.
+#ifdef SNMFNAT_WS_PROBE
+__device__ unsigned long long g_ws_probe[16];
+#define WS_TICK(i)                                                       \
+  do {                                                                   \
+    if (probe) {                                                         \
+      const long long t_ = clock64();                                    \
+      atomicAdd(&g_ws_probe[i], (unsigned long long)(t_ - tprev));       \
+      tprev = t_;                                                        \
+    }                                                                    \
+  } while (0)
+#else
+#define WS_TICK(i) do {} while (0)
+#endif
+
 template <int KT, int CL, int TPC, bool VSMEM>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__((TPC + 1) * 32, VSMEM ? 1 : 2)
 wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr, int has_trace, int g_step,
@@ -543,6 +558,10 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   if (!st.do_update[slot]) return;  // uniform over the cluster
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SNMFNAT_WS_PROBE
+  const bool probe = (blockIdx.x % (4 * 37)) == 0 && tid == 0;
+  long long tprev = clock64();
+#endif
   const int g = lane >> 2, tg = lane & 3;
   const int F = d.F, LDF = d.LDF, R_a = d.R_a, R_d = d.R_d, n = d.m_a;
   const double flr = sc.flr;
@@ -685,7 +704,9 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
     ++rnd;
     __syncthreads();
   };
+  WS_TICK(0);
   cluster.sync();  // the mbarriers of every CTA are initialised before anybody pushes
+  WS_TICK(1);
 
   // column norms of init_w (sparse_nmf.m:158)
   warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
@@ -711,6 +732,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   __syncthreads();
   double hsum_all = 0.0;
   for (int k = 0; k < Ru; ++k) hsum_all += hs_s[k];
+  WS_TICK(2);
 
   // ---- multiplicative updates ----
   int it = 0;
@@ -783,6 +805,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
           }
         }
     }
+    WS_TICK(3);
     // column reductions: cw_k = sum_f w, s_k = sum_f G.*w                               :215-221
     warp_partial(0, [&](int j, int e) { return w[j][e]; });
     warp_partial(1, [&](int j, int e) { return gacc[j][e] * w[j][e]; });
@@ -790,6 +813,10 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
     if (lane == 0) scratch[warp] = cacc;
     double div = 0.0;
     cluster_combine(2, true, &div);
+    WS_TICK(4);
+#ifdef SNMFNAT_WS_PROBE
+    if (probe) atomicAdd(&g_ws_probe[8], 1ull);
+#endif
     bool stop = false;
     if (want_cost) {
       cost = div + sc.sparsity * hsum_all;                                               // :261
@@ -815,6 +842,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         gacc[j][e] = 0.0;
       }
     // column normalisation                                                              :242
+    WS_TICK(5);
     warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
     cluster_combine(1, false, nullptr, true);
 #pragma unroll
@@ -825,7 +853,9 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         if (k < Ru) w[j][e] = w[j][e] * tot[k];
       }
     ++it;
+    WS_TICK(6);
   }
+  WS_TICK(9);
 
   // ---- B_DFT_d = [B_rem, B_new, B_fix]  (bnmf_sep_event_RT_IS16.m:336) into the other buffer ----
   const int n_rem = R_a - Ru;
@@ -853,7 +883,12 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
     atomicAdd(&st.stats[2], (unsigned long long)it);
     if (has_trace) tr.info[(st.frame_base[slot] + g_step) * 4 + 3] = it;
   }
+  WS_TICK(7);
   cluster.sync();  // peers may still be reading this CTA's exchange buffers
+  WS_TICK(10);
+#ifdef SNMFNAT_WS_PROBE
+  if (probe) atomicAdd(&g_ws_probe[15], 1ull);
+#endif
   if (rank == 0 && tid == 0) st.bd_sel[slot] = sel ^ 1;
 }
 
@@ -887,6 +922,19 @@ void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScala
   else launch_wsolve_variant<8, 4, 16, true>(ctx, d, sc, st, t, tr ? 1 : 0, n_active, g_step, tab);
   count_launch(ctx);
   check_launch(ctx, "wsolve_fast_kernel");
+#ifdef SNMFNAT_WS_PROBE
+  static int nl = 0;
+  if (++nl == 140) {
+    SN_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long pr[16];
+    SN_CUDA(cudaMemcpyFromSymbol(pr, g_ws_probe, sizeof(pr)));
+    const double nk = (double)(pr[15] ? pr[15] : 1), ni = (double)(pr[8] ? pr[8] : 1);
+    fprintf(stderr, "snmfnat ws probe (%.0f solves, %.1f GEMM passes per solve), clk per solve: staging issue %.0f | cluster.sync %.0f | "
+            "norms+H scaling %.0f | epilogue %.0f | final cluster.sync %.0f ; clk per pass: GEMMs %.0f | reductions+combine %.0f | "
+            "W update %.0f | norm combine %.0f\n", nk, ni / nk, pr[0] / nk, pr[1] / nk, pr[2] / nk, (pr[9] + pr[7]) / nk, pr[10] / nk,
+            pr[3] / ni, pr[4] / ni, pr[5] / ni, pr[6] / ni);
+  }
+#endif
 }
 
 }  // namespace snmfnat

@@ -224,6 +224,10 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   const int FT = MS_CL * MS_ROWS;                                        // index of the tail row
   const double flr = sc.flr;
 
+#ifdef SNMFNAT_MS_PROBE
+  const bool probe = blockIdx.x == 0 && tid == 0;
+  long long tprev = clock64();
+#endif
   extern __shared__ __align__(1024) double smem[];
   double* Wp = smem + L::off_Wp;
   double* hS = smem + L::off_hS;
@@ -336,8 +340,11 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     const int slot = slot_s[n];
     WnP[i] = (tail_rank && slot >= 0) ? st.Bd[st.bd_sel[slot]][((size_t)slot * d.R_d + k) * LDF + FT] : 0.0;
   }
+  MS_TICK(12);
   asm volatile("cp.async.wait_all;" ::: "memory");
+  MS_TICK(13);
   cluster.sync();   // barriers initialised everywhere, local buffers staged
+  MS_TICK(9);
 
   // ---- exchange: every value is pushed by the lane that produced it (st.async; the receiver's mbarrier counts the bytes) ----
   unsigned parRS = 0, parAG = 0;
@@ -471,10 +478,7 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     return warp_sum(s);
   };
 
-#ifdef SNMFNAT_MS_PROBE
-  const bool probe = blockIdx.x == 0 && tid == 0;
-  long long tprev = clock64();
-#endif
+  MS_TICK(10);
   for (;;) {
     hf_mbar_wait_bounded(barAG, parAG);
     MS_TICK(0);
@@ -674,6 +678,10 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     }
   }
   cluster.sync();  // nobody may exit while a peer can still push into its shared memory
+  MS_TICK(11);
+#ifdef SNMFNAT_MS_PROBE
+  if (probe) atomicAdd(&g_ms_probe[15], 1ull);
+#endif
 }
 
 // ---- host side ----
@@ -731,6 +739,10 @@ void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars
     fprintf(stderr, "snmfnat ms probe (clk per iteration over %.0f iterations): waitAG %.0f | passA %.0f | bar1 %.0f | ratio+bar2 %.0f | "
             "passB+push %.0f | waitRS %.0f | owner+pushrow %.0f\n", it, pr[0] / it, pr[1] / it, pr[2] / it, pr[3] / it, pr[4] / it,
             pr[5] / it, pr[6] / it);
+    const double nk = (double)(pr[15] ? pr[15] : 1);
+    fprintf(stderr, "snmfnat ms probe (clk per kernel, cluster 0, %.0f kernels): issue staging %.0f | cp.async wait %.0f | cluster.sync %.0f | "
+            "init exchange %.0f | epilogue %.0f | iterations per kernel %.1f\n", nk, pr[12] / nk, pr[13] / nk, pr[9] / nk, pr[10] / nk,
+            pr[11] / nk, it / nk);
   }
 #endif
 }
