@@ -51,6 +51,43 @@ def _cpu_worker(args):
     return idx, len(pcm) / FS, time.perf_counter() - t0, int(np.abs(out.astype(np.int64)).sum())
 
 
+def _parity_worker(args):
+    """Oracle result of one whole utterance of the timed batch (checker only, outside every timed region)."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    idx, pcm, ad = args
+    from oracle import snmf_oracle as O
+    import bench_workload as W
+    fx = W.load_fixtures()
+    out, _ = O.enhance_utterance(pcm, O.default_params(), fx["B_x"], fx["B_d"], h_init=fx["h_init"], Ad_blk_init=ad)
+    return idx, out
+
+
+def parity_spot_check(pcms, ads, gpu_out, out_off, out_len, n_check=4):
+    """Compare the enhanced PCM of `n_check` utterances OF THE TIMED BATCH (the shortest ones, so that the oracle stays
+    cheap) with the float64 oracle.  Returns the dict that goes into the JSON line."""
+    import multiprocessing as mp
+    order = np.argsort([len(x) for x in pcms], kind="stable")[:n_check]
+    jobs = [(int(u), np.ascontiguousarray(pcms[u]), ads[u]) for u in order]
+    with mp.get_context("spawn").Pool(len(jobs)) as pool:
+        res = pool.map(_parity_worker, jobs, chunksize=1)
+    worst_lsb, worst_snr, lens_ok = 0, float("inf"), True
+    for u, ref in res:
+        got = gpu_out[out_off[u]: out_off[u] + out_len[u]]
+        lens_ok &= len(got) == len(ref)
+        n = min(len(got), len(ref))
+        d = got[:n].astype(np.int64) - ref[:n].astype(np.int64)
+        worst_lsb = max(worst_lsb, int(np.abs(d).max()) if n else 0)
+        e = float(np.sum(d.astype(np.float64) ** 2))
+        pw = float(np.sum(ref[:n].astype(np.float64) ** 2))
+        worst_snr = min(worst_snr, 10 * np.log10(pw / e) if e > 0 else float("inf"))
+    return {"checker": "oracle/snmf_oracle.py (float64 NumPy port), whole utterances of the timed batch",
+            "utterances": [int(u) for u in order], "audio_s": [len(pcms[u]) / FS for u in order],
+            "lengths_equal": bool(lens_ok), "max_abs_diff_lsb": worst_lsb,
+            "min_snr_db": None if worst_snr == float("inf") else worst_snr,
+            "ok": bool(lens_ok and worst_lsb <= 1)}
+
+
 def _cpu_warm(i):
     from oracle import snmf_oracle as O  # noqa: F401
     import bench_workload as W
@@ -301,8 +338,69 @@ def run_ours(args, rank, world, local_rank):
     prof = batch.profile()
     batch.set_profile(False)
 
+    out_host = pin_out.numpy().copy() if rank == 0 else None
+    out_lens = np.asarray(batch.out_lengths, dtype=np.int64)
+    batch.close()
+    del batch
+
+    # ---- strong scaling (BASELINE.json configs[2] as written: ONE corpus of `utts` utterances sharded over the ranks by
+    #      se_snmf_nat_b200.sharding.shard_utterances, longest-processing-time first; no data-path collective)
+    strong = None
+    if world > 1:
+        from se_snmf_nat_b200 import sharding
+        c_pcms, c_ads, _ = W.make_batch(args.utts, rank=0, device=dev)      # the same corpus on every rank
+        c_lens = [len(x) for x in c_pcms]
+        mine = sharding.shard_utterances(c_lens, world)[rank]
+        sb = api.Batch(ctx, p, fx["B_x"], fx["B_d"], np.array([c_lens[i] for i in mine], dtype=np.int64), fx["h_init"],
+                       np.stack([c_ads[i] for i in mine]))
+        sb.upload([c_pcms[i] for i in mine])
+        sb.set_groups(args.groups)
+        sb.run()
+        ctx.sync()
+        s_steps = max(1, min(args.steps, 3))
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize(); ctx.sync()
+        s0.record(stream)
+        for _ in range(s_steps):
+            sb.run()
+        s1.record(stream)
+        ctx.sync(); torch.cuda.synchronize(); barrier()
+        ms_strong = max_over_ranks(float(s0.elapsed_time(s1))) / s_steps
+        own_ms = float(s0.elapsed_time(s1)) / s_steps
+        strong = {"value": float(sum(c_lens)) / FS / (ms_strong / 1e3), "unit": UNIT, "ms_per_step": ms_strong, "steps": s_steps,
+                  "utterances_total": args.utts, "utterances_this_rank": len(mine),
+                  "fastest_rank_ms": -max_over_ranks(-own_ms),
+                  "note": "one corpus split over the ranks (strong scaling); `value` above is the weak-scaling figure"}
+        sb.close()
+        del sb, c_pcms, c_ads
+
+    # ---- BASELINE.json configs[3] in the same line: dictionary training on 1.25 M frames per GPU (weak), K = 256, NCCL
+    #      all-reduce of the F x K accumulators attached when there is more than one rank
+    train = None
+    if not args.no_train:
+        import bench_train
+        ta = argparse.Namespace(train_k=256, train_frames=args.train_frames, train_scaling="weak", steps=20, warmup=3)
+        try:
+            tl = bench_train.measure(ta, rank, world, local_rank, ClockSampler, measured_peaks)
+            if tl is not None:
+                train = {"metric": tl["metric"], "iters_per_s": tl["value"], "ms_per_iteration": tl["ms_per_step"],
+                         "frames_total": tl["config"]["frames_total"], "frames_per_gpu": tl["config"]["frames_per_gpu"],
+                         "K": tl["config"]["K"], "nranks": world, "scaling": "weak",
+                         "tflops_per_gpu": tl["roofline"]["achieved"], "tf32_peak_cublas_measured": tl["roofline"]["peak"],
+                         "frac": tl["roofline"]["frac"], "kernel_ms": tl["kernel_ms"], "e2e_iters_per_s": tl["e2e"]["value"],
+                         "objective": tl["objective"], "clocks": tl["clocks"],
+                         "collective": "ncclAllReduce of F*Kp+Kp floats per iteration" if world > 1 else "none (1 rank)"}
+        except Exception as ex:  # the headline must survive a failure of the extra leg
+            train = {"error": repr(ex)}
+
     if rank != 0:
         return
+    # ---- the timed batch against the oracle (4 whole utterances, outside every timed region)
+    parity = None
+    if world == 1 and not args.no_parity:
+        off = np.concatenate([[0], np.cumsum(out_lens)[:-1]])
+        parity = parity_spot_check(pcms, ads, out_host, off, out_lens)
     # ---- roofline of the dominant kernel class (device time from CUDA events on the launch stream)
     pk = measured_peaks()
     F, R, m_a = 513, 200, 100
@@ -390,6 +488,7 @@ def run_ours(args, rank, world, local_rank):
         "stats": {k: stats[k] for k in ("hops", "h_iters", "w_iters", "gated_hops", "w_solves", "w_atoms", "launches")},
         "algorithmic_tflops": stats["flops"] * world / (ms_step / 1e3) / 1e12,
         "output_checksum": checksum, "workload_gen_s": t_gen,
+        "parity_check": parity, "strong_scaling": strong, "train": train,
     }
     print(json.dumps(line), flush=True)
 
@@ -402,6 +501,8 @@ def main():
     ap.add_argument("--utts", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the embedded dictionary-training leg (configs[3])")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check of the timed batch")
     ap.add_argument("--groups", type=int, default=int(os.environ.get("SNMFNAT_GROUPS", "3")),
                     help="interleaved slot groups on separate CUDA streams (scheduling only)")
     ap.add_argument("--workload", default="enhance", choices=["enhance", "train", "latency"],

@@ -58,11 +58,13 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   }
   std::vector<int32_t> chain;
   if (nrhs > 5 && !mxIsEmpty(prhs[5])) for (size_t i = 0; i < n; ++i) chain.push_back((int32_t)mxGetPr(prhs[5])[i]);
-  // RNG on the host: H init after rand('seed',.), then one rand(R_a, m_a) per file like init_buff.m:38
+  // RNG on the host: H init after rand('seed',.), then per file the two draws of init_buff.m:37-38 in their order:
+  // g.A_d = rand(R_d, m) (overwritten before its first use, but it advances the generator) and g.Ad_blk = rand(R_a, m_a)
   seed_rng(p);
   mxArray* h0 = host_rand(R, 1);
   std::vector<double> ad((size_t)n * q.R_a * q.m_a);
   for (size_t i = 0; i < n; ++i) {
+    mxDestroyArray(host_rand(q.R_d, 1));
     mxArray* a = host_rand(q.R_a, q.m_a);
     std::memcpy(ad.data() + i * q.R_a * q.m_a, mxGetPr(a), sizeof(double) * q.R_a * q.m_a);
     mxDestroyArray(a);

@@ -790,10 +790,17 @@ def park_miller(n, state=1):
     return out
 
 
-def default_rng_inputs(p, R=None):
-    """Deterministic stand-ins for the MATLAB RNG draws (see tests/golden)."""
+def default_rng_inputs(p, R=None, with_A_d=False):
+    """Deterministic stand-ins for the MATLAB RNG draws (see tests/golden).
+
+    init_buff.m:37-38 draws ``g.A_d = rand(R_d, m)`` BEFORE ``g.Ad_blk = rand(R_a, m_a)``; the stream keeps that order
+    (the A_d values are overwritten before their first use, so only their position in the stream matters).
+    tests/golden/ref_shadow/rand.m replays the same stream / the same Park-Miller sequence inside Octave or MATLAB."""
     R = p['R_x'] + p['R_d'] if R is None else R
     h_init = park_miller(R, 1)
     rs = np.random.RandomState(5489)
+    A_d = rs.rand(p['R_d'])
     Ad = rs.rand(p['m_a'], p['R_a']).T.copy()
+    if with_A_d:
+        return h_init, Ad, A_d
     return h_init, Ad

@@ -320,6 +320,13 @@ int snmfnat_batch_run(snmfnat_batch* b) {
     SN_CUDA(cudaEventRecord(b->fork_ev, ctx->stream));
     for (int q = 0; q < NG; ++q) SN_CUDA(cudaStreamWaitEvent(b->gstream[q], b->fork_ev, 0));
   }
+  // the launch helpers read ctx->stream: point it at the group's stream inside the loop and restore it on EVERY exit path
+  // (a throwing launch must not leave the shared context on a stream that snmfnat_batch_destroy is about to destroy)
+  struct StreamGuard {
+    snmfnat_ctx* c;
+    cudaStream_t saved;
+    ~StreamGuard() { c->stream = saved; }
+  } stream_guard{ctx, ctx->stream};
   cudaStream_t main_stream = ctx->stream;
   for (int g = 0; g < b->max_hops; ++g) {
     const int na = b->active_at[g];

@@ -8,8 +8,9 @@ What it writes
   bases.npz        B_DFT_x / B_DFT_d / B_Mel_x / B_Mel_d of basis/*/TASLP_Splice0-SNMF_p2_DD0/R_100.mat (MAT v5)
   wavs.npz         int16 samples (44-byte header stripped) of the reference's wav/ inputs and its two shipped
                    outputs (*_out_v3.9_18.wav), the only end-to-end golden vectors the reference holds
-  rng_seed1.npz    the stand-ins for MATLAB's RNG draws (h_init = rand(200,1) after rand('seed',1),
-                   Ad_blk = rand(50,100)); see oracle.snmf_oracle.default_rng_inputs
+  rng_seed1.npz    the stand-ins for MATLAB's RNG draws (h_init = rand(200,1) after rand('seed',1), then in the order of
+                   init_buff.m:37-38 A_d = rand(100,1), Ad_blk = rand(50,100)); see oracle.snmf_oracle.default_rng_inputs
+  rng_seed1.mat    the same stream as MAT v5 for tests/golden/ref_shadow/rand.m (make_ref_vectors.m)
   M03_oracle.npz   the float64 oracle's own result on M03 (output, per-hop iteration counts / gates, a few
                    activations, final noise basis) -- pins the oracle against regressions
 """
@@ -38,8 +39,11 @@ def main():
         wavs[key] = O.read_wav_pcm(REF / "wav" / f"{name}.wav")
     np.savez_compressed(OUT / "wavs.npz", **wavs)
     p = O.default_params()
-    h_init, Ad = O.default_rng_inputs(p)
-    np.savez_compressed(OUT / "rng_seed1.npz", h_init=h_init, Ad_blk=Ad)
+    h_init, Ad, A_d = O.default_rng_inputs(p, with_A_d=True)
+    np.savez_compressed(OUT / "rng_seed1.npz", h_init=h_init, Ad_blk=Ad, A_d=A_d)
+    # the same draws for tests/golden/ref_shadow/rand.m (Octave / MATLAB): init_buff.m:37-38 order, column-major
+    scipy.io.savemat(OUT / "rng_seed1.mat", {"stream": np.concatenate([A_d, Ad.T.ravel()])[:, None], "h_init": h_init[:, None]},
+                     format="5")
     tr = []
     out, g = O.enhance_utterance(wavs["M03_in"], p, bx["B_DFT_sub"], bd["B_DFT_sub"], h_init=h_init, Ad_blk_init=Ad,
                                  trace=tr)

@@ -213,6 +213,32 @@ def test_per_hop_stream_matches_oracle_and_batch(api, O, bases, wavs, rng_inputs
 
 
 @pytest.mark.parametrize("mel", [False, True], ids=["run_basis_DNMF", "run_basis_DNMF_Mel"])
+def test_per_hop_stream_three_event_classes(api, O, bases, wavs, rng_inputs):
+    """EVENT_NUM = 3, EVENT_RANK = [1 21 41] (initial_setting_Proposed_Techwin_201603_RT.m:40-49): the per-class
+    reconstructions x_hat_i of bnmf_sep_event_RT_IS16.m:159-164,373-380 come back class by class."""
+    h_init, Ad = rng_inputs
+    over = dict(EVENT_NUM=3, EVENT_RANK=[1, 21, 41])
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    pcm = wavs["M04_in"][12000:12000 + 160 * 45]
+    Bx, Bd = bases["B_DFT_x"], bases["B_DFT_d"]
+    g = api.init_buff(Bx, Bd, Bx, Bd, p, Ad_blk_init=Ad)
+    go = O.init_buff(Bx, Bd, Bx, Bd, po, Ad_blk_init=Ad)
+    y = np.zeros(640)
+    for l in range(1, len(pcm) // 160 + 1):
+        y = np.concatenate([y[160:], pcm[(l - 1) * 160:l * 160].astype(float)])
+        aux = l >= 30
+        xh, dh, xt, g = api.bnmf_sep_event_RT_IS16(y, l, g, p, h_init=h_init, nargout=3 if aux else 1)
+        xho, dho, xto, go = O.bnmf_sep_event_RT_IS16(y, l, go, po, h_init=h_init, want_aux=aux)
+        assert int(g["stats"][0]) == go.dbg["h_iters"], l
+        assert np.max(np.abs(xt - xto)) <= 1e-6 * max(1.0, np.max(np.abs(xto))), l
+        if aux:
+            assert xh.shape == (3, 1, 640)
+            for i in range(3):
+                assert np.max(np.abs(xh[i, 0] - xho[i])) <= 1e-6 * max(1.0, np.max(np.abs(xho))), (l, i)
+    g.close() if hasattr(g, "close") else None
+
+
 def test_dnmf_basis_retraining_matches_oracle(api, O, wavs, mel):
     """run_basis_DNMF.m / run_basis_DNMF_Mel.m: STFT of clean, noise and mixture, activations of
     the mixture with the dictionary fixed, then W-only updates of the two halves -- every step on the GPU."""

@@ -67,6 +67,25 @@ def test_m03_full_parity(api, O, bases, wavs, rng_inputs, m03_oracle):
     b.close()
 
 
+def test_gpu_matches_reference_vectors(api, bases, wavs):
+    """The CUDA path against the UNMODIFIED reference (tests/golden/ref_vectors.mat, see make_ref_vectors.m); skipped
+    until the file exists (no Octave / MATLAB in the build image or on the GPU boxes)."""
+    from conftest import GOLDEN
+    f = GOLDEN / "ref_vectors.mat"
+    if not f.exists():
+        pytest.skip("tests/golden/ref_vectors.mat not generated (needs GNU Octave or MATLAB)")
+    import scipy.io
+    from oracle import snmf_oracle as Or
+    ref = scipy.io.loadmat(f, squeeze_me=True, struct_as_record=False)["ref"]
+    h_init, Ad = Or.default_rng_inputs(Or.default_params())
+    b, outs = run_gpu_traced(api, api.default_p(), [wavs["M03_in"]], bases, h_init, Ad)
+    assert rel_err(np.asarray(ref.Xm_tilde).T, b.trace(0, "Xm_tilde")) <= SPEC_TOL
+    assert rel_err(np.asarray(ref.A_d).T, b.trace(0, "A")[:, 100:]) <= SPEC_TOL
+    assert rel_err(ref.B_DFT_d_final, b.noise_basis(0)) <= SPEC_TOL
+    assert snr_db(np.asarray(ref.out_pcm, dtype=np.float64), outs[0]) >= WAVE_SNR_DB
+    b.close()
+
+
 def test_ragged_batch_equals_single_runs(api, O, bases, wavs, rng_inputs):
     """Utterances of different length (including empty and shorter than one hop) in one batch give exactly what
     each gives alone, and what the oracle gives."""
@@ -87,7 +106,8 @@ def test_ragged_batch_equals_single_runs(api, O, bases, wavs, rng_inputs):
         assert np.array_equal(alone, outs[i]), "batch composition changed a result"
 
 
-@pytest.mark.parametrize("variant", ["wiener", "no_adapt", "no_blk", "maxiter25_gap5", "preemph", "R_a20_ma40"])
+@pytest.mark.parametrize("variant", ["wiener", "no_adapt", "no_blk", "maxiter25_gap5", "preemph", "R_a20_ma40",
+                                     "overlap0.1_ma40", "overlap0.5_ma40", "event3"])
 def test_settings_variants(api, O, bases, wavs, rng_inputs, variant):
     """The knobs the reference's settings/bak_IS16_results variants change are runtime parameters."""
     h_init, Ad = rng_inputs
@@ -98,11 +118,19 @@ def test_settings_variants(api, O, bases, wavs, rng_inputs, variant):
         "maxiter25_gap5": dict(max_iter=25, blk_gap=5),
         "preemph": dict(preemph=0.92),
         "R_a20_ma40": dict(R_a=20, m_a=40),
+        # settings/initial_setting_SNMF.m:57-58: an update only every floor(overlap_m_a * m_a) = 4 / 20 gated hops
+        # (the update_switch counting of bnmf_sep_event_RT_IS16.m:293,343-345)
+        "overlap0.1_ma40": dict(m_a=40, overlap_m_a=0.1),
+        "overlap0.5_ma40": dict(m_a=40, overlap_m_a=0.5),
+        # settings/bak_IS16_results/initial_setting_Proposed_Techwin_201603_RT.m:40-49: three event classes
+        "event3": dict(EVENT_NUM=3, EVENT_RANK=[1, 21, 41]),
     }[variant]
     p = dict(api.default_p(), **over)
     po = dict(O.default_params(), **over)
     if variant == "R_a20_ma40":
         Ad = np.random.RandomState(11).rand(20, 40)
+    if variant.startswith("overlap"):
+        Ad = np.random.RandomState(12).rand(50, 40)
     pcm = wavs["M03_in"][8000:8000 + 160 * 120]
     out = api.enhance_batch([pcm], p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad)[0]
     ref, _ = O.enhance_utterance(pcm, po, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad)

@@ -16,15 +16,62 @@ def test_oracle_matches_reference_golden_wav_M03(bases, wavs, rng_inputs, m03_or
     gold = wavs["M03_ref_out"]
     # exact output length: (floor(N/160)+1)*160   (filewise_run_IS16.m:146,162-165)
     assert len(out) == len(gold) == (len(wavs["M03_in"]) // 160 + 1) * 160 == 55040
-    # coarse end-to-end pin: the shipped output was made with MATLAB RNG streams we cannot regenerate; the
-    # pipeline's hard gates make 15-25 dB the achievable agreement
-    assert snr_db(gold, out) > 20.0
+    # coarse end-to-end pin: the shipped output was made with MATLAB RNG streams we cannot regenerate; four other RNG
+    # streams give 21.7 .. 24.1 dB against it, so 21 dB is as tight as this pin can be (see the negative controls below)
+    assert snr_db(gold, out) > 21.0
     # the oracle's own committed result: bit-exact regression pin
     assert np.array_equal(out, m03_oracle["out"])
     assert np.array_equal([t["h_iters"] for t in tr], m03_oracle["h_iters"])
     assert np.array_equal([t["R_a_up"] for t in tr], m03_oracle["R_a_up"])
     # first init_N_len frames are (almost) silence: G = 1e-9 (bnmf_sep_event_RT_IS16.m:256-259)
     assert np.all(np.abs(out[:160 * 10].astype(int)) <= 1)
+
+
+@pytest.mark.parametrize("wrong", [dict(alpha_d=0.7), dict(adapt_train_N=0), dict(beta=0.5), dict(alpha_p=0.5)],
+                         ids=lambda d: "-".join(f"{k}={v}" for k, v in d.items()))
+def test_golden_wav_pin_detects_wrong_parameters(bases, wavs, rng_inputs, wrong):
+    """Negative controls: what the end-to-end pin CAN see.  A wrong noise-smoothing constant, no adaptation, a wrong
+    over-subtraction weight or a wrong a-priori SNR smoothing all fall below the 21 dB the shipped settings reach.
+    (It cannot see max_iter, conv_eps, sparsity, alpha_eta or blk_gap: their effect is inside the 21.7 .. 24.1 dB spread
+    of the RNG stream.  Parity with the reference at kernel granularity needs tests/golden/make_ref_vectors.m.)"""
+    p = O.default_params()
+    p.update(wrong)
+    h_init, Ad = rng_inputs
+    out, _ = O.enhance_utterance(wavs["M03_in"], p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad)
+    assert snr_db(wavs["M03_ref_out"], out) < 21.0
+
+
+def test_oracle_matches_reference_golden_wav_LM_in(bases, wavs, rng_inputs):
+    """The second wav pair the reference ships (LM_in, 17.7 s): length rule and the coarse SNR pin."""
+    p = O.default_params()
+    h_init, Ad = rng_inputs
+    out, _ = O.enhance_utterance(wavs["LM_in"], p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad)
+    assert len(out) == len(wavs["LM_ref_out"])
+    assert snr_db(wavs["LM_ref_out"], out) > 16.0
+
+
+def test_oracle_matches_reference_vectors(bases, wavs):
+    """Hop-level pin against the UNMODIFIED reference run under Octave / MATLAB with the RNG replaced by the committed
+    stream (tests/golden/make_ref_vectors.m + ref_shadow/rand.m).  Skipped until somebody with an interpreter commits
+    tests/golden/ref_vectors.mat: neither exists in the build image nor on the GPU boxes (profiles/r02_octave_probe.txt)."""
+    from conftest import GOLDEN, rel_err
+    f = GOLDEN / "ref_vectors.mat"
+    if not f.exists():
+        pytest.skip("tests/golden/ref_vectors.mat not generated (needs GNU Octave or MATLAB)")
+    import scipy.io
+    ref = scipy.io.loadmat(f, squeeze_me=True, struct_as_record=False)["ref"]
+    p = O.default_params()
+    h_init, Ad, A_d = O.default_rng_inputs(p, with_A_d=True)
+    tr = []
+    out, g = O.enhance_utterance(wavs["M03_in"], p, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad,
+                                 A_d_init=A_d, trace=tr)
+    assert len(tr) == int(ref.hops)
+    Xt = np.stack([t["Xm_tilde"] for t in tr], axis=1)
+    Ad_hop = np.stack([t["A"][p["R_x"]:] for t in tr], axis=1)
+    assert rel_err(ref.Xm_tilde, Xt) <= 1e-3          # north_star: spectra within 1e-3
+    assert rel_err(ref.A_d, Ad_hop) <= 1e-3           # activations within 1e-3
+    assert rel_err(ref.B_DFT_d_final, g.B_DFT_d) <= 1e-3
+    assert snr_db(np.asarray(ref.out_pcm, dtype=np.float64), out) >= 40.0   # waveform >= 40 dB
 
 
 def test_oracle_lm_in_length_rule(wavs):
