@@ -207,7 +207,9 @@ def measure(args, rank, world, local_rank, ClockSampler, measured_peaks):
                                     "(MEASURED_PEAKS.json holds no TF32 figure)",
                      "half_of_measured_bf16_sustained": pk.get("bf16_tflops_sustained", 0.0) / 2.0},
         "kernel_ms": prof,
-        "objective": {"first": float(cost[0]), "last": float(cost[-1]), "non_increasing": bool(np.all(np.diff(cost) <= 1e-6 * cost[:-1]))},
+        "objective": {"first": float(cost[0]), "last": float(cost[-1]), "max_rel_increase": float(np.max(np.diff(cost) / cost[:-1])),
+                      "non_increasing": bool(np.all(np.diff(cost) <= 1e-5 * cost[:-1])),
+                      "note": "fp32 accumulators: increases below 1e-5 relative are summation noise near convergence"},
         "w_checksum": float(np.abs(w).sum()), "workload_gen_s": t_gen,
     }
     tr.close()

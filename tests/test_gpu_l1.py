@@ -212,7 +212,6 @@ def test_per_hop_stream_matches_oracle_and_batch(api, O, bases, wavs, rng_inputs
     g.close()
 
 
-@pytest.mark.parametrize("mel", [False, True], ids=["run_basis_DNMF", "run_basis_DNMF_Mel"])
 def test_per_hop_stream_three_event_classes(api, O, bases, wavs, rng_inputs):
     """EVENT_NUM = 3, EVENT_RANK = [1 21 41] (initial_setting_Proposed_Techwin_201603_RT.m:40-49): the per-class
     reconstructions x_hat_i of bnmf_sep_event_RT_IS16.m:159-164,373-380 come back class by class."""
@@ -239,6 +238,7 @@ def test_per_hop_stream_three_event_classes(api, O, bases, wavs, rng_inputs):
     g.close() if hasattr(g, "close") else None
 
 
+@pytest.mark.parametrize("mel", [False, True], ids=["run_basis_DNMF", "run_basis_DNMF_Mel"])
 def test_dnmf_basis_retraining_matches_oracle(api, O, wavs, mel):
     """run_basis_DNMF.m / run_basis_DNMF_Mel.m: STFT of clean, noise and mixture, activations of
     the mixture with the dictionary fixed, then W-only updates of the two halves -- every step on the GPU."""

@@ -151,3 +151,82 @@ def test_unsupported_configurations_fail_loudly(api):
     assert e.value.code == -4
     with pytest.raises(api.SnmfnatError):
         api.basis_train_core(np.ones((8, 8)), 2, [0, 1], dict(cf="is", sparsity=0, max_iter=1, conv_eps=0), h_init=np.ones((2, 8)))
+
+
+def test_long_run_drift_against_float64_oracle(api, O):
+    """TF32 operands over many iterations at a size closer to production (T = 16 384 frames, 60 iterations): W, H and
+    the cost must stay inside north_star's 1e-3 of the float64 oracle, not merely be non-increasing."""
+    F, K, T, iters = 513, 64, 16384, 60
+    V, idx, H0 = make_problem(F, K, T, seed=5, ktrue=48)
+    w_ref, h_ref, obj = oracle_run(O, V, idx, H0, iters)
+    tr = api.Train(api.get_context(0), F, K, T, 5.0)
+    try:
+        tr.set_data(V, V[:, idx], H0)
+        out = tr.iterate(iters, want_cost=True)
+        w, h = tr.get_w(), tr.get_h()
+    finally:
+        tr.close()
+    ew, eh = rel_err(w_ref, w), rel_err(h_ref, h)
+    print(f"60 iterations at T=16384: rel err W {ew:.2e}, H {eh:.2e}, cost {abs(out['cost'][-1] / obj['cost'][-1] - 1):.2e}")
+    assert ew < TOL and eh < TOL, (ew, eh)
+    np.testing.assert_allclose(out["cost"], obj["cost"], rtol=TOL)
+
+
+_NCCL_RANK_SCRIPT = r"""
+import os, sys, time, numpy as np
+rank, world, tmp = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+os.environ["CUDA_VISIBLE_DEVICES"] = str(rank)
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from se_snmf_nat_b200 import api
+from test_gpu_train import make_problem
+F, K, T, iters = 513, 64, 2000, 6
+V, idx, H0 = make_problem(F, K, T, seed=21)
+uid_file = os.path.join(tmp, "uid.bin")
+if rank == 0:
+    uid = api.Train.nccl_unique_id()
+    open(uid_file + ".tmp", "wb").write(uid); os.replace(uid_file + ".tmp", uid_file)
+else:
+    for _ in range(600):
+        if os.path.exists(uid_file): break
+        time.sleep(0.1)
+    uid = open(uid_file, "rb").read()
+lo, hi = rank * T // world, (rank + 1) * T // world          # contiguous frame shard (sharding.frame_ranges)
+tr = api.Train(api.get_context(0), F, K, hi - lo, 5.0)
+tr.attach_nccl(uid, rank, world)
+tr.set_data(V[:, lo:hi], V[:, idx], H0[:, lo:hi])
+out = tr.iterate(iters, want_cost=True)
+np.savez(os.path.join(tmp, f"rank{{rank}}.npz"), w=tr.get_w(), h=tr.get_h(), cost=out["cost"])
+tr.close()
+print("rank", rank, "ok")
+"""
+
+
+def test_frame_sharded_training_over_nccl_equals_single_gpu(api, O, tmp_path):
+    """frames split over two ranks (one process per GPU), ONE ncclAllReduce of the F x K + K
+    accumulators per iteration (snmfnat_train_attach_nccl), every rank applies the same W update.  The result must equal
+    the single-GPU run up to the fp32 summation order of the accumulators."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    F, K, T, iters = 513, 64, 2000, 6
+    V, idx, H0 = make_problem(F, K, T, seed=21)
+    one = api.Train(api.get_context(0), F, K, T, 5.0)
+    try:
+        one.set_data(V, V[:, idx], H0)
+        c1 = one.iterate(iters, want_cost=True)["cost"]
+        w1, h1 = one.get_w(), one.get_h()
+    finally:
+        one.close()
+    script = _NCCL_RANK_SCRIPT.format(root=str(ROOT))
+    procs = [subprocess.Popen([sys.executable, "-c", script, str(r), "2", str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert np.array_equal(r0["w"], r1["w"])                       # replicated W update: bit-identical on both ranks
+    assert rel_err(w1, r0["w"]) < 1e-5, rel_err(w1, r0["w"])
+    assert rel_err(h1, np.concatenate([r0["h"], r1["h"]], axis=1)) < 1e-5
+    np.testing.assert_allclose(r0["cost"], c1, rtol=1e-5)
