@@ -188,7 +188,10 @@ int snmfnat_batch_create(snmfnat_ctx* ctx, const snmfnat_params* p, const double
 int snmfnat_batch_destroy(snmfnat_batch* b);
 /* Host -> device copy of the PCM of every utterance (pcm[u] has len[u] samples). */
 int snmfnat_batch_upload(snmfnat_batch* b, const int16_t* const* pcm);
-/* Same, from one contiguous (preferably pinned) buffer holding the utterances back to back. */
+/* Same, from one contiguous (preferably pinned) buffer holding the utterances back to back.  ASYNCHRONOUS on the context
+ * stream, unlike snmfnat_batch_upload: the copies are only queued when the call returns, so pcm_packed must stay valid
+ * and unmodified until the next synchronising call on this context (snmfnat_ctx_sync, snmfnat_batch_download*, ...).
+ * A caller that refills or frees the buffer earlier feeds undefined PCM into the run. */
 int snmfnat_batch_upload_packed(snmfnat_batch* b, const int16_t* pcm_packed);
 /* Reset the per-stream state to init_buff and enhance every utterance; inputs and outputs stay in HBM.
  * Asynchronous on the context stream; snmfnat_ctx_sync() or a download waits for it. */
@@ -254,6 +257,16 @@ int snmfnat_enhance_batch(snmfnat_ctx* ctx, const snmfnat_params* p, const doubl
                           const int16_t* const* pcm, const int64_t* len, const int32_t* chain_id,
                           const double* h_init, const double* Ad_blk_init, int64_t ad_stride,
                           int16_t* const* out);
+
+/* The same on n_dev GPUs of one node from ONE host process (what a single MATLAB / Octave process binds
+ * for Do_MultiBatch_IS16_20160324_CHiME4.m:202-208 / run_ntf_sep_RT.m:9-41): utterances, or chains of utterances, are
+ * split over devices[0..n_dev) longest-processing-time first; one host thread and one context per device; no collective.
+ * Arguments as snmfnat_enhance_batch (indices of pcm / len / chain_id / Ad_blk_init / out are corpus indices). */
+int snmfnat_enhance_batch_multi(const int* devices, int n_dev, const snmfnat_params* p, const double* win_stft,
+                                const double* win_istft, const double* B_x, const double* B_d, int n2, int n_utt,
+                                const int16_t* const* pcm, const int64_t* len, const int32_t* chain_id,
+                                const double* h_init, const double* Ad_blk_init, int64_t ad_stride,
+                                int16_t* const* out);
 
 /* ---- offline dictionary training (run_basis_train.m:80-91,112-116) ---------------------- */
 

@@ -1,8 +1,9 @@
 // MEX gateway: [x_hat_i, d_hat_i, x_tilde, g] = bnmf_sep_event_RT_IS16(y, l, g, p)
 // replaces src/bnmf_sep_event_RT_IS16.m:1-423.  The struct g produced by the reference's own init_buff.m is accepted
 // unchanged: on the first hop its fields seed a device-resident stream whose handle is stored in g.snmfnat_handle;
-// the fields later read by the callers (g.B_DFT_d / g.B_Mel_d: src/NTF_sep_event_RT.m:137-138, SE_GUI.m) are
-// refreshed on every hop, the rest stay on the device (snmfnat_stream_get reads them on demand).
+// g.B_DFT_d, the field the callers read back (src/NTF_sep_event_RT.m:137-138, SE_GUI.m), is refreshed on every hop, the
+// rest stays on the device (snmfnat_stream_get reads it on demand).  A g that arrives with l == 1 starts a new file:
+// the stream it carried (if any) is destroyed first, so a corpus loop does not accumulate device state.
 #include <map>
 #include "snmfnat_mex.h"
 using namespace snmex;
@@ -27,9 +28,16 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   mxArray* g = mxDuplicateArray(gin);          // value semantics: never write prhs
   snmfnat_stream* s = nullptr;
   const mxArray* hf = field(g, "snmfnat_handle");
-  if (hf && l > 1) {
+  if (hf) {
     auto it = streams().find(*(uint64_t*)mxGetData(hf));
-    if (it != streams().end()) s = it->second;
+    if (it != streams().end()) {
+      if (l > 1) {
+        s = it->second;
+      } else {   // the caller re-used a struct of a finished file: release its device state
+        snmfnat_stream_destroy(it->second);
+        streams().erase(it);
+      }
+    }
   }
   if (!s) {  // first hop of a stream: build the device state from the reference-made g (src/init_buff.m:17-62)
     const mxArray *Bmx = field(g, "B_Mel_x"), *Bmd = field(g, "B_Mel_d"), *Bx = field(g, "B_DFT_x"), *Bd = field(g, "B_DFT_d");

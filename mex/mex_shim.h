@@ -1,6 +1,6 @@
-/* Minimal declarations of the MATLAB / Octave MEX C API, ONLY for syntax- and ABI-checking the gateways in a container
- * that has neither MATLAB nor Octave (compile with -DSNMFNAT_MEX_SHIM).  With a real toolchain (`mex` or `mkoctfile
- * --mex`) the real <mex.h> is used instead. */
+/* Minimal declarations of the MATLAB / Octave MEX C API for a container that has neither MATLAB nor Octave (compile with
+ * -DSNMFNAT_MEX_SHIM).  mex_host.cpp IMPLEMENTS them (a small working host: `make host`), so the gateways are linked and
+ * executed by tests/test_mex_host.py.  With a real toolchain (`mex` or `mkoctfile --mex`) the real <mex.h> is used instead. */
 #ifndef SNMFNAT_MEX_SHIM_H_
 #define SNMFNAT_MEX_SHIM_H_
 #include <stddef.h>
@@ -42,6 +42,9 @@ mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
 mxArray* mxCreateNumericMatrix(mwSize, mwSize, mxClassID, mxComplexity);
 mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
 mxArray* mxCreateString(const char*);
+mxArray* mxCreateLogicalMatrix(mwSize, mwSize);
+mxArray* mxCreateCellMatrix(mwSize, mwSize);
+void mxSetCell(mxArray*, mwIndex, mxArray*);
 char* mxArrayToString(const mxArray*);
 void mxFree(void*);
 void mxDestroyArray(mxArray*);
@@ -50,6 +53,8 @@ int mexCallMATLAB(int, mxArray**, int, mxArray**, const char*);
 void mexLock(void);
 int mexAtExit(void (*)(void));
 int mexPrintf(const char*, ...);
+/* the gateway entry point has C linkage, as in the real <mex.h> */
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]);
 #ifdef __cplusplus
 }
 #endif

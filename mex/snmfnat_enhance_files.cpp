@@ -71,6 +71,21 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   }
   const mxArray *ws = field(p, "win_STFT"), *wi = field(p, "win_ISTFT");
   if (!ws || !wi) mexErrMsgIdAndTxt("snmfnat:param", "p.win_STFT / p.win_ISTFT missing");
+  // p.gpus = [0 1 2 ...] (optional): the files are split over these devices, one host thread per device
+  // (Do_MultiBatch_IS16_20160324_CHiME4.m:202-208 walks the corpus file by file; the files are independent)
+  const mxArray* gp = field(p, "gpus");
+  if (gp && mxGetNumberOfElements(gp) > 1 && q.B_sep_mode != SNMFNAT_SEP_MEL) {
+    std::vector<int> dev;
+    for (size_t i = 0; i < mxGetNumberOfElements(gp); ++i) dev.push_back((int)mxGetPr(gp)[i]);
+    const int rcm = snmfnat_enhance_batch_multi(dev.data(), (int)dev.size(), &q, mxGetPr(ws), mxGetPr(wi),
+                                                mat(prhs[2], F, q.R_x, "B_DFT_x"), mat(prhs[3], F, q.R_d, "B_DFT_d"), (int)F,
+                                                (int)n, pin.data(), len.data(), chain.empty() ? nullptr : chain.data(),
+                                                mxGetPr(h0), ad.data(), (int64_t)q.R_a * q.m_a, pout.data());
+    mxDestroyArray(h0);
+    check(rcm);
+    for (size_t i = 0; i < n; ++i) write_wav(po[i], out[i], q.fs);
+    return;
+  }
   snmfnat_batch* bt = nullptr;
   check(snmfnat_batch_create(ctx(), &q, mxGetPr(ws), mxGetPr(wi), mat(prhs[2], F, q.R_x, "B_DFT_x"),
                              mat(prhs[3], F, q.R_d, "B_DFT_d"), (int)F, (int)n, len.data(),

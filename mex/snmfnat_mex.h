@@ -7,6 +7,7 @@
 #include "mex.h"
 #endif
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -22,10 +23,12 @@ inline void at_exit() {
   if (ctx_slot()) snmfnat_ctx_destroy(ctx_slot());
   ctx_slot() = nullptr;
 }
-// One context per MATLAB process; no CPU fallback: a missing device is an error.
+// One context per MATLAB process (device = $SNMFNAT_DEVICE, default 0); no CPU fallback: a missing device is an error.
+// Multi-GPU corpus runs go through snmfnat_enhance_batch_multi, which creates one context per device itself.
 inline snmfnat_ctx* ctx() {
   if (!ctx_slot()) {
-    if (snmfnat_ctx_create(0, &ctx_slot()) != 0) mexErrMsgIdAndTxt("snmfnat:device", "%s", snmfnat_last_error(nullptr));
+    const char* e = std::getenv("SNMFNAT_DEVICE");
+    if (snmfnat_ctx_create(e ? std::atoi(e) : 0, &ctx_slot()) != 0) mexErrMsgIdAndTxt("snmfnat:device", "%s", snmfnat_last_error(nullptr));
     mexLock();
     mexAtExit(at_exit);
   }

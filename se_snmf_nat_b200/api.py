@@ -231,7 +231,8 @@ class Batch:
         check(self._lib.snmfnat_batch_upload(self._h, ptrs))
 
     def upload_packed(self, packed_ptr: int):
-        """``packed_ptr``: address of a (pinned) host buffer with the utterances back to back."""
+        """``packed_ptr``: address of a (pinned) host buffer with the utterances back to back.  Asynchronous: the buffer
+        must stay valid and unmodified until the next synchronising call (``ctx.sync()``, ``download*``)."""
         check(self._lib.snmfnat_batch_upload_packed(self._h, C.cast(packed_ptr, C.POINTER(C.c_int16))))
 
     def enable_trace(self, on=True):

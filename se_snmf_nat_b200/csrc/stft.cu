@@ -252,10 +252,29 @@ void launch_ola_int16(snmfnat_ctx* ctx, const StftGeom& g, const UttTables& ut, 
 // ---------------------------------------------------------------------------------------------------
 void FftPlans::create(snmfnat_ctx* ctx, int n, long long frames) {
   destroy();
-  SN_REQUIRE(frames > 0 && frames < (1ll << 31), SNMFNAT_EINVAL, "bad frame count %lld", frames);
-  int nn[1] = {n};
-  SN_CUFFT(cufftPlanMany(&fwd, 1, nn, nullptr, 1, n, nullptr, 1, n / 2 + 1, CUFFT_D2Z, (int)frames));
-  SN_CUFFT(cufftPlanMany(&inv, 1, nn, nullptr, 1, n / 2 + 1, nullptr, 1, n, CUFFT_Z2D, (int)frames));
+  SN_REQUIRE(frames > 0 && frames < (1ll << 40), SNMFNAT_EINVAL, "bad frame count %lld", frames);
+  // 64-bit plans: frames * n passes 2^31 elements at about 2 700 CHiME-length utterances in one batch
+  long long nn[1] = {n};
+  size_t ws_f = 0, ws_i = 0;
+  SN_CUFFT(cufftCreate(&fwd));
+  cufftResult rf = cufftMakePlanMany64(fwd, 1, nn, nullptr, 1, n, nullptr, 1, n / 2 + 1, CUFFT_D2Z, frames, &ws_f);
+  if (rf != CUFFT_SUCCESS) {
+    cufftDestroy(fwd);
+    fwd = 0;
+    fail(rf == CUFFT_ALLOC_FAILED ? SNMFNAT_ENOMEM : SNMFNAT_EUNSUPPORTED,
+         "cuFFT cannot plan %lld transforms of length %d in one batch (cufft error %d): split the corpus into smaller batches",
+         frames, n, (int)rf);
+  }
+  SN_CUFFT(cufftCreate(&inv));
+  cufftResult ri = cufftMakePlanMany64(inv, 1, nn, nullptr, 1, n / 2 + 1, nullptr, 1, n, CUFFT_Z2D, frames, &ws_i);
+  if (ri != CUFFT_SUCCESS) {
+    cufftDestroy(fwd);
+    cufftDestroy(inv);
+    fwd = inv = 0;
+    fail(ri == CUFFT_ALLOC_FAILED ? SNMFNAT_ENOMEM : SNMFNAT_EUNSUPPORTED,
+         "cuFFT cannot plan %lld inverse transforms of length %d in one batch (cufft error %d): split the corpus into smaller batches",
+         frames, n, (int)ri);
+  }
   SN_CUFFT(cufftSetStream(fwd, ctx->stream));
   SN_CUFFT(cufftSetStream(inv, ctx->stream));
   nf = frames;

@@ -17,6 +17,8 @@ struct snmfnat_stream {
   DevBuf<double2> Yc;
   FftPlans fft;
   int last_l = 0;
+  // DFT mode with a "B_Mel_d" slot that differs from B_DFT_d (bnmf_sep_event_RT_IS16.m:328 [sic]): see snmfnat_stream_create
+  bool fix_from_mel = false, fix_synced = false;
 };
 
 namespace snmfnat {
@@ -95,7 +97,14 @@ int snmfnat_stream_create(snmfnat_ctx* ctx, const snmfnat_params* p, const doubl
   SN_CUDA(cudaMemcpy(s->sb.win_stft.p, win_stft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
   SN_CUDA(cudaMemcpy(s->sb.win_istft.p, win_istft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
   s->sb.reset(ctx);
-  if (B_Mel_d && B_Mel_d != B_DFT_d) upload_basis(ctx, B_DFT_d, c.d.F, c.d.R_d, c.d.LDF, s->sb.Bd0.p);
+  if (B_Mel_d && B_Mel_d != B_DFT_d) {
+    // The adaptable atoms (columns < R_a) start from B_DFT_d; the never-updated ones stay B_Mel_d(:, R_a+1:end) in BOTH
+    // ping-pong buffers: the reference re-assembles [B_rem, B_new, B_Mel_d(:, R_a+1:end)] on every update (:328,336), so
+    // from the first update on the fixed columns are B_Mel_d's whatever B_DFT_d held there.  Before the first update the
+    // H-solve reads B_DFT_d as given, hence buffer 0 (the active one) takes all of it.
+    upload_basis(ctx, B_DFT_d, c.d.F, c.d.R_d, c.d.LDF, s->sb.Bd0.p);
+    s->fix_from_mel = true;
+  }
   const int nh = INT_MAX;
   const long long fb = 0;
   SN_CUDA(cudaMemcpy(s->sb.n_hops.p, &nh, sizeof(int), cudaMemcpyHostToDevice));
@@ -197,9 +206,17 @@ int snmfnat_stream_step(snmfnat_stream* s, const double* y, int l, const double*
     for (int i = 0; i < p.NOISE_NUM; ++i)
       if (d_hat_i) istft_one(s, s->cls.p + (size_t)(p.EVENT_NUM + i) * c.d.LDF, d_hat_i + (size_t)i * c.g.sz);
   }
-  int flag = 0;
+  int flag = 0, sel = 0;
   SN_CUDA(cudaMemcpyAsync(&flag, s->sb.err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (s->fix_from_mel && !s->fix_synced) SN_CUDA(cudaMemcpyAsync(&sel, s->sb.bd_sel.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   SN_CUDA(cudaStreamSynchronize(st));
+  if (sel == 1) {
+    // first update done: from now on the never-updated columns are B_Mel_d's in both buffers (the W-solve only rewrites
+    // columns < R_a, so buffer 0 still carries B_DFT_d's fixed columns until they are replaced here, before its next use)
+    const size_t off = (size_t)c.d.R_a * c.d.LDF, cnt = (size_t)(c.d.R_d - c.d.R_a) * c.d.LDF;
+    SN_CUDA(cudaMemcpyAsync(s->sb.Bd0.p + off, s->sb.Bd_fix.p + off, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    s->fix_synced = true;
+  }
   SN_REQUIRE(flag == 0, SNMFNAT_ENUMERIC,
              "an all-zero activation row was selected for adaptation (bnmf_sep_event_RT_IS16.m:292 vs :323)");
   s->last_l = l;

@@ -295,3 +295,31 @@ def test_gist_ntf_matches_oracle(api, O, variant_c, with_a):
         Cr2, _, or2 = O.gist_ntf(dict(p, cost_check=0, max_iter=5), B, S, rand=rand, variant_c=True)
         assert og2["iters"] == or2["iters"] == 5 and og2["cost"].size == 0
         assert rel_err(Cr2, Cg2) < 1e-9
+
+
+def test_stream_fixed_columns_follow_the_mel_slot_after_updates(api, O, bases, wavs, rng_inputs):
+    """bnmf_sep_event_RT_IS16.m:328 [sic]: even in DFT mode the never-updated noise atoms are re-assembled from
+    g.B_Mel_d(:, R_a+1:end) on every update.  With a B_Mel_d slot that DIFFERS from B_DFT_d the fixed columns therefore
+    switch to B_Mel_d's at the first update and must stay there over later updates (both ping-pong buffers)."""
+    h_init, Ad = rng_inputs
+    p = api.default_p()
+    po = O.default_params()
+    rs = np.random.RandomState(17)
+    Bx, Bd = bases["B_DFT_x"], bases["B_DFT_d"]
+    Bmel = Bd * np.exp(0.2 * rs.randn(*Bd.shape))            # a different "B_Mel_d" slot of the same shape
+    g = api.init_buff(Bx, Bmel, Bx, Bd, p, Ad_blk_init=Ad)
+    go = O.init_buff(Bx, Bmel, Bx, Bd, po, Ad_blk_init=Ad)
+    pcm = wavs["M03_in"][8000:8000 + 160 * 60]
+    y = np.zeros(640)
+    updates = 0
+    for l in range(1, 61):
+        y = np.concatenate([y[160:], pcm[(l - 1) * 160:l * 160].astype(float)])
+        _, _, xt, g = api.bnmf_sep_event_RT_IS16(y, l, g, p, h_init=h_init, nargout=1)
+        _, _, xto, go = O.bnmf_sep_event_RT_IS16(y, l, go, po, h_init=h_init)
+        updates += int(go.dbg["w_iters"] > 0)
+        assert int(g["stats"][0]) == go.dbg["h_iters"], l
+        assert np.max(np.abs(xt - xto)) <= 1e-6 * max(1.0, np.max(np.abs(xto))), l
+    assert updates >= 3
+    assert rel_err(go.B_DFT_d, g["B_DFT_d"]) < 1e-9
+    assert rel_err(Bmel[:, 50:], g["B_DFT_d"][:, 50:]) < 1e-12
+    g.close()
