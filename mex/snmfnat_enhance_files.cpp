@@ -19,7 +19,19 @@ static std::vector<int16_t> read_pcm(const std::string& path) {
   std::fclose(f);
   return v;
 }
-static void write_wav(const std::string& path, const std::vector<int16_t>& x, int fs) {
+// src/pcm2wav.m:9-10: out./32767 through wavwrite(..., 16, ...) = round(x * 32768), half away from zero, clipped
+static std::vector<int16_t> pcm2wav_samples(const std::vector<int16_t>& v) {
+  std::vector<int16_t> y(v.size());
+  for (size_t i = 0; i < v.size(); ++i) {
+    const double x = (double)v[i] / 32767.0 * 32768.0;
+    double r = x < 0 ? -std::floor(-x + 0.5) : std::floor(x + 0.5);
+    r = r > 32767.0 ? 32767.0 : (r < -32768.0 ? -32768.0 : r);
+    y[i] = (int16_t)r;
+  }
+  return y;
+}
+static void write_wav(const std::string& path, const std::vector<int16_t>& raw, int fs) {
+  const std::vector<int16_t> x = pcm2wav_samples(raw);
   FILE* f = std::fopen(path.c_str(), "wb");
   if (!f) mexErrMsgIdAndTxt("snmfnat:io", "cannot create %s", path.c_str());
   const uint32_t data = (uint32_t)x.size() * 2, riff = 36 + data, fmt = 16, rate = fs, brate = fs * 2;

@@ -130,6 +130,8 @@ SIGNATURES = {
     "snmfnat_batch_get_noise_basis": (C.c_int, [_vp, C.c_int, _dp]),
     "snmfnat_enhance_batch": (C.c_int, [_vp, _P(Params), _dp, _dp, _dp, _dp, C.c_int, C.c_int, _i16pp,
                                         _P(C.c_int64), _P(C.c_int32), _dp, _dp, C.c_int64, _i16pp]),
+    "snmfnat_enhance_batch_multi": (C.c_int, [_P(C.c_int), C.c_int, _P(Params), _dp, _dp, _dp, _dp, C.c_int, C.c_int, _i16pp,
+                                              _P(C.c_int64), _P(C.c_int32), _dp, _dp, C.c_int64, _i16pp]),
     "snmfnat_train_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_int, _P(_vp)]),
     "snmfnat_train_destroy": (C.c_int, [_vp]),
     "snmfnat_train_nccl_unique_id": (C.c_int, [_vp]),

@@ -311,10 +311,47 @@ def enhance_batch(pcms: Sequence[np.ndarray], p: dict, B_x, B_d, *, h_init, Ad_b
         b.close()
 
 
+def enhance_batch_multi(pcms: Sequence[np.ndarray], p: dict, B_x, B_d, *, h_init, Ad_blk_init, devices: Sequence[int],
+                        chain_id=None):
+    """The same corpus on several GPUs of one node from this one process (snmfnat_enhance_batch_multi): utterances /
+    chains are split over ``devices`` longest first, one host thread per device, no collective."""
+    lib = _lib.load()
+    ps = params_struct(p)
+    arrs = [np.ascontiguousarray(x, dtype=np.int16) for x in pcms]
+    n = len(arrs)
+    lens = np.array([a.size for a in arrs], dtype=np.int64)
+    hop, delay = int(p["frameshift"]), int(p["delay"])
+    outs = [np.empty(int((ln // hop + delay + 1 - delay) * hop), dtype=np.int16) for ln in lens]
+    i16p = C.POINTER(C.c_int16)
+    pin = (i16p * n)(*[a.ctypes.data_as(i16p) for a in arrs])
+    pout = (i16p * n)(*[a.ctypes.data_as(i16p) for a in outs])
+    Bx, Bd = _f64(B_x), _f64(B_d)
+    ad = np.ascontiguousarray(np.stack([_f64(a).ravel(order="F") for a in np.broadcast_to(
+        np.asarray(Ad_blk_init, dtype=np.float64), (n,) + np.asarray(Ad_blk_init).shape[-2:])]))
+    ch = None if chain_id is None else np.ascontiguousarray(chain_id, dtype=np.int32)
+    dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+    ws, wi, h0 = _f64(p["win_STFT"]).ravel(), _f64(p["win_ISTFT"]).ravel(), _f64(h_init).ravel()
+    check(lib.snmfnat_enhance_batch_multi(dev, len(devices), C.byref(ps), _dptr(ws), _dptr(wi), _dptr(Bx), _dptr(Bd),
+                                          Bx.shape[0], n, pin, lens.ctypes.data_as(C.POINTER(C.c_int64)),
+                                          None if ch is None else ch.ctypes.data_as(C.POINTER(C.c_int32)), _dptr(h0),
+                                          _dptr(ad), ad.shape[1], pout))
+    return outs
+
+
+def pcm2wav_samples(pcm: np.ndarray) -> np.ndarray:
+    """src/pcm2wav.m:9-10: the raw int16 output is divided by 32767 and written with wavwrite(..., 16, ...), which
+    quantises as round(x * 32768) (half away from zero) clipped to [-32768, 32767]: samples above 16383 in magnitude
+    move by one LSB."""
+    x = np.asarray(pcm, dtype=np.float64) / 32767.0 * 32768.0
+    y = np.sign(x) * np.floor(np.abs(x) + 0.5)
+    return np.clip(y, -32768, 32767).astype(np.int16)
+
+
 def filewise_run_IS16(path_in: str, path_denoise: str, p: dict, B_DFT_x, B_DFT_d, *, h_init, Ad_blk_init,
                       device: int = 0):
-    """filewise_run_IS16.m:54-186 for one file: read the int16 samples after the 44-byte header (:92-97),
-    enhance, write raw PCM wrapped as a 16-bit WAV (src/pcm2wav.m)."""
+    """filewise_run_IS16.m:54-186 for one file: read the int16 samples after the 44-byte header (:92-97), enhance,
+    then src/pcm2wav.m: the PCM goes to a 16-bit WAV through wavwrite's x/32767*32768 re-quantisation.  Returns the raw
+    int16 output of the frame loop (what fwrite puts into the file before pcm2wav, :165)."""
     raw = np.fromfile(path_in, dtype="<i2")
     pcm = raw[22:]
     out = enhance_batch([pcm], p, B_DFT_x, B_DFT_d, h_init=h_init, Ad_blk_init=Ad_blk_init, device=device)[0]
@@ -323,7 +360,7 @@ def filewise_run_IS16(path_in: str, path_denoise: str, p: dict, B_DFT_x, B_DFT_d
         w.setnchannels(1)
         w.setsampwidth(2)
         w.setframerate(int(p.get("fs", 16000)))
-        w.writeframes(out.astype("<i2").tobytes())
+        w.writeframes(pcm2wav_samples(out).astype("<i2").tobytes())
     return out
 
 

@@ -85,3 +85,12 @@ def test_mel_matrix_matches_the_oracle():
         assert a.shape == b.shape and np.array_equal(a, b)
     M = api.mel_matrix(16000, 64, 1024)
     assert M.min() == 0.0 and M.max() == 1.0 and np.all(M.sum(0) > 0)
+
+
+def test_pcm2wav_requantisation():
+    """src/pcm2wav.m:9-10 + wavwrite: round(s / 32767 * 32768), half away from zero, clipped to int16."""
+    import numpy as np
+    from se_snmf_nat_b200 import api
+    s = np.array([0, 1, -1, 100, 16383, 16384, -16384, 20000, -20000, 32766, 32767, -32767, -32768], dtype=np.int16)
+    want = [0, 1, -1, 100, 16383, 16385, -16385, 20001, -20001, 32767, 32767, -32768, -32768]
+    assert api.pcm2wav_samples(s).tolist() == want
