@@ -107,7 +107,18 @@ def test_bnmf_sep_event_gateway_hop_loop_matches_oracle(host, bases, wavs, rng_i
     for file_no, off in enumerate((16000, 40000)):
         pcm = wavs["LM_in"][off:off + 160 * 40]
         go = O.init_buff(Bx, Bd, Bx, Bd, po, Ad_blk_init=Ad)
-        g = host.mx(g0) if file_no == 0 else g      # the second file re-uses the struct the first one returned
+        if file_no == 0:
+            g = host.mx(g0)
+        else:
+            # the next file: a fresh init_buff struct, but still carrying the handle field of the previous file (what a
+            # MATLAB loop that rebuilds g field by field would hand over): the gateway must release that stream
+            old = host.py(g)["snmfnat_handle"]
+            L.mxDestroyArray(g)
+            g = host.mx(g0)
+            hnd = L.mxCreateNumericArray(2, (C.c_size_t * 2)(1, 1), mexhost.UINT64, 0)
+            C.memmove(L.mxGetData(hnd), np.asarray(old, dtype=np.uint64).ctypes.data, 8)
+            L.mxAddField(g, b"snmfnat_handle")
+            L.mxSetField(g, 0, b"snmfnat_handle", hnd)
         y = np.zeros(640)
         for l in range(1, 41):
             y = np.concatenate([y[160:], pcm[(l - 1) * 160:l * 160].astype(float)])
