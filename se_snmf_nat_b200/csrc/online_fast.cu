@@ -9,7 +9,9 @@
 //   Per MU iteration: 3 block barriers + 1 cluster barrier; the R-vector g, the cost partial and the tail
 //   terms travel through distributed shared memory.
 //
-// wsolve_fast_kernel : 4-CTA cluster per stream, 17 warps per CTA, one 8-row FP64 tensor-core tile per warp
+// wsolve_fast_kernel : 4-CTA cluster per stream, 17 warps per CTA, one 8-row FP64 tensor-core tile per warp (the 17th
+//   warp of the last CTA takes the F % 8 leftover rows with plain FMAs: a whole tensor-core tile for one row would give
+//   one scheduler of that SM a fifth tile, and every exchange of the cluster would wait for it)
 //   (mma.sync m8n8k4.f64).  W and G = (V./Lambda) H' fragments stay in registers for the whole solve in the SAME
 //   fragment layout (the k order of the first GEMM is permuted to match the accumulator layout of the second), the
 //   CTA's slice of V = lambda_d_blk is staged once in shared memory, H is staged once.  Padding rows/columns are
@@ -489,7 +491,7 @@ struct WfLayout {
   static constexpr int XN = 3 * KMAX + 8;
   static constexpr int WARPS = TPC + 1;      // TPC tile warps + 1 warp for the leftover tile
   int NP, HSd, VS, VROWS;
-  size_t off_H, off_V, off_red, off_recv, off_hs, off_wn, off_tot, off_tab, off_scratch, off_bar, bytes;
+  size_t off_H, off_V, off_red, off_recv, off_hs, off_wn, off_tot, off_tab, off_scratch, off_bar, off_Wl, off_Gl, off_rl, bytes;
   __host__ __device__ WfLayout(int m_a) {
     NP = (m_a + 15) / 16 * 16;
     HSd = NP + ((2 - NP % 8) + 8) % 8;          // == 2 (mod 8): conflict-free fragment loads in both GEMMs
@@ -507,6 +509,9 @@ struct WfLayout {
     off_tab = o;     o += 256;
     off_scratch = o; o += 64;
     off_bar = o;     o += 2;                        // 2 mbarriers
+    off_Wl = o;      o += 8 * KMAX;                 // leftover rows (F % 8 < 8) of W, G and the ratio: plain FMAs on one warp
+    off_Gl = o;      o += 8 * KMAX;
+    off_rl = o;      o += 8 * NP;
     bytes = o * sizeof(double);
   }
 };
@@ -559,7 +564,13 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef SNMFNAT_WS_PROBE
-  const bool probe = (blockIdx.x % (4 * 37)) == 0 && tid == 0;
+#ifndef SNMFNAT_WS_PROBE_RANK
+#define SNMFNAT_WS_PROBE_RANK 0
+#endif
+#ifndef SNMFNAT_WS_PROBE_TID
+#define SNMFNAT_WS_PROBE_TID 0
+#endif
+  const bool probe = (blockIdx.x % (4 * 37)) == SNMFNAT_WS_PROBE_RANK && tid == SNMFNAT_WS_PROBE_TID;
   long long tprev = clock64();
 #endif
   const int g = lane >> 2, tg = lane & 3;
@@ -602,10 +613,14 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   int tile_local = warp;                               // local tile index 0..TPC
   bool tile_valid;
   if (warp < TPC) tile_valid = (rank * TPC + warp) < NFT;
-  else tile_valid = (nleft > 0) && (rank == CL - 1);
+  else tile_valid = false;                             // the leftover rows do not use a tensor-core tile (see left_warp)
+  const bool left_warp = (warp == TPC) && (rank == CL - 1) && nleft > 0;
   int frow = row0 + tile_local * 8 + g;                // global row of this lane's fragment row
   if (warp == TPC) frow = NFT * 8 + g;
   const bool row_valid = tile_valid && frow < F;
+  double* Wl = smem + L.off_Wl;                        // [nleft][KMAX]
+  double* Gl = smem + L.off_Gl;
+  double* rl = smem + L.off_rl;                        // [nleft][NP] ratio of the leftover rows
   // local row index inside Vs: tiles 0..TPC-1 -> rows 0..8 TPC-1, leftover tile -> the 8 rows after them
   const int vrow = tile_local * 8 + g;
 
@@ -623,6 +638,11 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       if (row_valid && k < Ru) x = Bcur[(size_t)idx_up[k] * LDF + frow];
       w[j][e] = x;
       gacc[j][e] = 0.0;
+    }
+  if (left_warp)
+    for (int i = lane; i < nleft * KMAX; i += 32) {
+      const int r = i / KMAX, k = i - r * KMAX;
+      Wl[i] = (k < Ru) ? Bcur[(size_t)idx_up[k] * LDF + NFT * 8 + r] : 0.0;
     }
   if (tid < 128) tab[tid] = log_tab[tid];
   if (VSMEM) {
@@ -658,6 +678,15 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         const double s = rows8_sum_f(f(j, e));
         if (g == 0) rw[8 * j + 2 * tg + e] = s;
       }
+  };
+  // the same for the leftover rows: lanes <-> atoms, f(r, k)
+  auto left_partial = [&](int which, auto&& f) {
+    double* rw = red + ((size_t)which * WARPS + warp) * KMAX;
+    for (int k = lane; k < KMAX; k += 32) {
+      double s = 0.0;
+      for (int r = 0; r < nleft; ++r) s += f(r, k);
+      rw[k] = s;
+    }
   };
   // CTA partial (fixed warp order) PUSHED to the CTAs of the cluster (st.async, bytes counted on the receiver's
   // mbarrier: no cluster barrier / fence); totals in rank order -> tot[which][k]
@@ -709,10 +738,14 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   WS_TICK(1);
 
   // column norms of init_w (sparse_nmf.m:158)
-  warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
+  __syncwarp();
+  if (left_warp) left_partial(0, [&](int r, int k) { return Wl[r * KMAX + k] * Wl[r * KMAX + k]; });
+  else warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
   cluster_combine(1, false, nullptr);
   if (tid < KMAX) wn_s[tid] = (tid < Ru) ? sqrt(tot[tid]) : 1.0;
   __syncthreads();
+  if (left_warp)
+    for (int i = lane; i < nleft * KMAX; i += 32) Wl[i] = Wl[i] / wn_s[i % KMAX];
 #pragma unroll
   for (int j = 0; j < KT; ++j)
 #pragma unroll
@@ -806,9 +839,62 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         }
     }
     WS_TICK(3);
+    if (left_warp) {
+      // leftover rows: lambda / ratio with lanes <-> history columns (4 per lane), then G with lanes <-> atoms
+      for (int r = 0; r < nleft; ++r) {
+        const double* wr = Wl + r * KMAX;
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < Ru; ++k) {
+          const double wv = wr[k];
+          const double* hk = Hs + (size_t)k * HSd + lane;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (32 * q < NP) a[q] = fma(wv, hk[32 * q], a[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int t = lane + 32 * q;
+          if (t < NP) {
+            double rr = 0.0;
+            if (t < n) {
+              const double lam = fmax(a[q], flr);
+              const double v = fmax(Vs[(size_t)t * VS + TPC * 8 + r], flr);
+              rr = v * fast_rcp(lam);
+              if (want_cost) cacc += fma(v, fast_log(rr, tab), lam - v);
+            }
+            rl[r * NP + t] = rr;
+          }
+        }
+      }
+      __syncwarp();
+      for (int r = 0; r < nleft; ++r)
+        for (int k = lane; k < KMAX; k += 32) {
+          double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+          if (k < Ru) {
+            const double* hk = Hs + (size_t)k * HSd;
+            const double* rr = rl + r * NP;
+            for (int t = 0; t < NP; t += 4) {       // H is zero-padded up to NP, rl is zero beyond n
+              const double2 h01 = *reinterpret_cast<const double2*>(hk + t), h23 = *reinterpret_cast<const double2*>(hk + t + 2);
+              const double2 r01 = *reinterpret_cast<const double2*>(rr + t), r23 = *reinterpret_cast<const double2*>(rr + t + 2);
+              g0 = fma(r01.x, h01.x, g0);
+              g1 = fma(r01.y, h01.y, g1);
+              g2 = fma(r23.x, h23.x, g2);
+              g3 = fma(r23.y, h23.y, g3);
+            }
+          }
+          Gl[r * KMAX + k] = (g0 + g1) + (g2 + g3);
+        }
+      __syncwarp();
+    }
+    WS_TICK(3);
     // column reductions: cw_k = sum_f w, s_k = sum_f G.*w                               :215-221
-    warp_partial(0, [&](int j, int e) { return w[j][e]; });
-    warp_partial(1, [&](int j, int e) { return gacc[j][e] * w[j][e]; });
+    if (left_warp) {
+      left_partial(0, [&](int r, int k) { return Wl[r * KMAX + k]; });
+      left_partial(1, [&](int r, int k) { return Gl[r * KMAX + k] * Wl[r * KMAX + k]; });
+    } else {
+      warp_partial(0, [&](int j, int e) { return w[j][e]; });
+      warp_partial(1, [&](int j, int e) { return gacc[j][e] * w[j][e]; });
+    }
     cacc = warp_sum(cacc);
     if (lane == 0) scratch[warp] = cacc;
     double div = 0.0;
@@ -842,9 +928,25 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         gacc[j][e] = 0.0;
       }
     // column normalisation                                                              :242
+    if (left_warp) {
+      for (int i = lane; i < nleft * KMAX; i += 32) {
+        const int k = i % KMAX;
+        const double wv = Wl[i], hs = hs_s[k];
+        const double dpw = fmax(hs + tot[KMAX + k] * wv, flr);
+        const double dmw = Gl[i] + (hs * tot[k]) * wv;
+        Wl[i] = (k < Ru) ? wv * dmw * fast_rcp(dpw) : 0.0;
+      }
+      __syncwarp();
+    }
     WS_TICK(5);
-    warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
+    if (left_warp) left_partial(0, [&](int r, int k) { return Wl[r * KMAX + k] * Wl[r * KMAX + k]; });
+    else warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
     cluster_combine(1, false, nullptr, true);
+    if (left_warp)
+      for (int i = lane; i < nleft * KMAX; i += 32) {
+        const int k = i % KMAX;
+        if (k < Ru) Wl[i] = Wl[i] * tot[k];
+      }
 #pragma unroll
     for (int j = 0; j < KT; ++j)
 #pragma unroll
@@ -865,6 +967,11 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
     for (int e = 0; e < 2; ++e) {
       const int k = 8 * j + 2 * tg + e;
       if (row_valid && k < Ru) Bnext[(size_t)(n_rem + k) * LDF + frow] = w[j][e];
+    }
+  if (left_warp)
+    for (int i = lane; i < nleft * KMAX; i += 32) {
+      const int r = i / KMAX, k = i - r * KMAX;
+      if (k < Ru) Bnext[(size_t)(n_rem + k) * LDF + NFT * 8 + r] = Wl[i];
     }
   {
     // the not-updated adaptable atoms move to the front; columns >= R_a never change and are valid in both
