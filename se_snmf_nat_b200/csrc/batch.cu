@@ -280,12 +280,14 @@ int snmfnat_batch_run(snmfnat_batch* b) {
   auto mark = [&]() {
     if (prof) SN_CUDA(cudaEventRecord(b->ev[evi++], ctx->stream));
   };
+  NvtxRange nvtx_run("snmfnat_batch_run");
   mark();  // 0: start
   b->sb.reset(ctx);
   SN_CUDA(cudaMemcpyAsync(b->sb.l_offset.p, b->d_loff0.p, b->n_slots * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
   SN_CUDA(cudaMemcpyAsync(b->sb.n_hops.p, b->d_nhops0.p, b->n_slots * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
   const UttTables ut = utt_tables(b);
   // STFT of every frame
+  nvtxRangePushA("stft");
   launch_frame_pcm(ctx, c.g, ut, b->pcm.p, b->sb.win_stft.p, b->frames.p);
   SN_CUFFT(cufftExecD2Z(b->fft.fwd, b->frames.p, reinterpret_cast<cufftDoubleComplex*>(b->Yc.p)));
   launch_stft_post(ctx, c.g, b->Yc.p, b->NF, b->Ym.p, nullptr);
@@ -294,7 +296,9 @@ int snmfnat_batch_run(snmfnat_batch* b) {
     SN_REQUIRE(b->sb.mel(), SNMFNAT_EINVAL, "B_sep_mode='Mel': call snmfnat_batch_set_mel before snmfnat_batch_run");
     launch_mel_project(ctx, b->sb.melM.p, b->sb.n1, b->sb.LD1, c.d.F, c.d.LDF, b->Ym.p, b->NF, b->Ysep.p);
   }
+  nvtxRangePop();
   mark();  // 1: STFT done
+  nvtxRangePushA("hop loop: hsolve / gain / wsolve");
   // hop loop
   const SlotState st = b->sb.view();
   FrameArrays fr{b->Ym.p, b->Xt.p};
@@ -373,7 +377,9 @@ int snmfnat_batch_run(snmfnat_batch* b) {
       SN_CUDA(cudaEventRecord(b->gdone[q], b->gstream[q]));
       SN_CUDA(cudaStreamWaitEvent(main_stream, b->gdone[q], 0));
     }
+  nvtxRangePop();
   // ISTFT + overlap-add
+  NvtxRange nvtx_istft("istft + overlap-add");
   launch_istft_pre(ctx, c.g, b->Yc.p, b->Xt.p, b->NF);
   SN_CUFFT(cufftExecZ2D(b->fft.inv, reinterpret_cast<cufftDoubleComplex*>(b->Yc.p), b->frames.p));
   int windowed = 0;

@@ -102,6 +102,17 @@ struct snmfnat_ctx {
   std::string last_error;
 };
 
+// ---------------------------------------------------------------- NVTX ranges (header-only NVTX3; no-ops without a tool)
+#include <nvtx3/nvToolsExt.h>
+namespace snmfnat {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace snmfnat
+
 namespace snmfnat {
 inline void count_launch(snmfnat_ctx* ctx, int n = 1) { ctx->launches += n; }
 void check_launch(snmfnat_ctx* ctx, const char* what);

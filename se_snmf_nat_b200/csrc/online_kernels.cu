@@ -48,7 +48,11 @@ __host__ __device__ inline HsLayout hs_layout(int F, int R) {
   L.bytes = o * sizeof(double);
   return L;
 }
-size_t hsolve_smem_bytes(const OnlineDims& d) { return hs_layout(d.F, d.R).bytes; }
+// what the H-solve needs per CTA: the cluster-resident layout when it fits, else the streaming fallback's vectors
+size_t hsolve_smem_bytes(const OnlineDims& d) {
+  const size_t resident = hs_layout(d.F, d.R).bytes, streamed = ((size_t)5 * d.R + 2 * d.F + 64) * sizeof(double);
+  return resident < streamed ? resident : streamed;
+}
 
 // sum over the 32 lanes of p[i] for every i; lane L returns the total of p[L]
 __device__ __forceinline__ double transpose_reduce32(double (&p)[32], int lane) {
@@ -264,6 +268,126 @@ hsolve_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, cons
   cluster.sync();  // nobody may exit while a peer can still read its exchange buffers
 }
 
+
+// =====================================================================================================
+// H-solve for dictionaries that do not fit the shared memory of a 4-CTA cluster (R_x + R_d up to ~4000: the reference's
+// exemplar settings use 500 + 500, settings/bak_IS16_results/initial_setting_Exemplar.m:47-48): one CTA per stream, the
+// un-normalised basis is STREAMED from L2 / HBM twice per iteration (coalesced column reads), the column scaling of
+// sparse_nmf.m:157-160 is folded into the vectors (h / wn on the way in, g / wn on the way out).  Same update, cost and
+// stop rule as the resident kernels (sparse_nmf.m:186-283); a fallback, not a throughput path.
+// =====================================================================================================
+constexpr int HG_THREADS = 576;   // >= F for F = 513; thread <-> row in the Lambda pass
+constexpr int HG_WARPS = HG_THREADS / 32;
+
+__global__ void __launch_bounds__(HG_THREADS)
+hsolve_stream_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, const double* __restrict__ h_init, int g_step) {
+  const int slot = d.slot0 + (int)blockIdx.x * d.slot_stride;
+  const int l = g_step + 1 - st.l_offset[slot];
+  if (l < 1 || l > st.n_hops[slot]) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = d.F, R = d.R, R1 = d.R_x, LDF = d.LDF;
+  const double flr = sc.flr;
+  extern __shared__ __align__(16) double smem[];
+  double* h_s = smem;              // [R] activations (normalised-basis convention, sparse_nmf.m:160)
+  double* ht_s = h_s + R;          // [R] h ./ wn (what multiplies the raw columns)
+  double* iw_s = ht_s + R;         // [R] 1 / wn
+  double* dp_s = iw_s + R;         // [R] reciprocal of the H-update denominator (:192-193)
+  double* g_s = dp_s + R;          // [R]
+  double* v_s = g_s + R;           // [F]
+  double* r_s = v_s + F;           // [F]
+  double* scratch = r_s + F;       // [64]
+  const double* __restrict__ W1 = st.Bx;
+  const double* __restrict__ W2 = st.Bd[st.bd_sel[slot]] + (size_t)slot * d.R_d * LDF;
+  auto col = [&](int k) { return k < R1 ? W1 + (size_t)k * LDF : W2 + (size_t)(k - R1) * LDF; };
+  const double* __restrict__ V = fr.Ym + (size_t)(st.frame_base[slot] + g_step) * LDF;
+
+  for (int k = warp; k < R; k += HG_WARPS) {
+    const double* c = col(k);
+    double s1 = 0.0, s2 = 0.0;
+    for (int f = lane; f < F; f += 32) {
+      const double x = c[f];
+      s1 += x;
+      s2 = fma(x, x, s2);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      const double wn = sqrt(s2);
+      iw_s[k] = 1.0 / wn;
+      dp_s[k] = 1.0 / fmax(s1 / wn + sc.sparsity, flr);
+      h_s[k] = h_init[k] * wn;
+    }
+  }
+  for (int f = tid; f < F; f += HG_THREADS) v_s[f] = fmax(V[f], flr);          // sparse_nmf.m:169
+  __syncthreads();
+
+  // out[f] = sum_{k in [k0, k1)} W[f][k] * x[k] for this thread's row (coalesced over the threads of a warp)
+  auto row_dot = [&](const double* x, int k0, int k1, int f) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+      a0 = fma(col(k)[f], x[k], a0);
+      a1 = fma(col(k + 1)[f], x[k + 1], a1);
+      a2 = fma(col(k + 2)[f], x[k + 2], a2);
+      a3 = fma(col(k + 3)[f], x[k + 3], a3);
+    }
+    for (; k < k1; ++k) a0 = fma(col(k)[f], x[k], a0);
+    return (a0 + a1) + (a2 + a3);
+  };
+  int it = 0;
+  double last_cost = INFINITY, cost = 0.0;
+  for (;;) {
+    for (int k = tid; k < R; k += HG_THREADS) ht_s[k] = h_s[k] * iw_s[k];
+    __syncthreads();
+    double cterm = 0.0;
+    for (int f = tid; f < F; f += HG_THREADS) {
+      const double lam = fmax(row_dot(ht_s, 0, R, f), flr);
+      const double v = v_s[f];
+      r_s[f] = v / lam;
+      if (sc.cost_check && it >= 1) cterm += v * log(v / lam) - v + lam;        // :250
+    }
+    double hpart = 0.0;
+    for (int k = tid; k < R; k += HG_THREADS) hpart += h_s[k];
+    const double div = block_sum(cterm, scratch);      // also publishes r_s (block barriers inside)
+    const double hsum = block_sum(hpart, scratch);
+    for (int k = warp; k < R; k += HG_WARPS) {
+      const double* c = col(k);
+      double s = 0.0;
+      for (int f = lane; f < F; f += 32) s = fma(c[f], r_s[f], s);
+      s = warp_sum(s);
+      if (lane == 0) g_s[k] = s * iw_s[k];
+    }
+    bool stop = false;
+    if (sc.cost_check && it >= 1) {
+      cost = div + sc.sparsity * hsum;                                           // :261
+      if (it > 1 && sc.conv_eps > 0.0) {
+        const double e = fabs(cost - last_cost) / last_cost;                     // :274
+        if (e < sc.conv_eps) stop = true;
+      }
+      last_cost = cost;
+    }
+    if (it >= sc.max_iter) stop = true;
+    if (stop) break;
+    __syncthreads();
+    for (int k = tid; k < R; k += HG_THREADS) h_s[k] = h_s[k] * g_s[k] * dp_s[k];  // :195
+    ++it;
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int k = tid; k < R; k += HG_THREADS) st.A[(size_t)slot * R + k] = h_s[k];
+  if (tid == 0) {
+    st.h_iters[slot] = it;
+    st.h_cost[slot] = cost;
+  }
+  // reconstructions with the un-normalised bases (bnmf_sep_event_RT_IS16.m:174,197)
+  for (int f = tid; f < F; f += HG_THREADS) {
+    st.Xhat[(size_t)slot * LDF + f] = row_dot(h_s, 0, R1, f);
+    st.Dhat[(size_t)slot * LDF + f] = row_dot(h_s, R1, R, f);
+  }
+}
+
+static size_t hsolve_stream_smem(const OnlineDims& d) { return ((size_t)5 * d.R + 2 * d.F + 64) * sizeof(double); }
+
 bool force_generic() {
   static int v = -1;
   if (v < 0) {
@@ -297,6 +421,16 @@ void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& s
     return;
   }
   const HsLayout L = hs_layout(d.F, d.R);
+  if (d.R > HS_THREADS || (int)L.bytes > ctx->max_smem_optin || (L.RS + 31) / 32 > 5) {
+    // dictionary too large for the cluster-resident kernels: stream it (Exemplar / Techwin settings of the reference)
+    const size_t sm = hsolve_stream_smem(d);
+    SN_REQUIRE((int)sm <= ctx->max_smem_optin, SNMFNAT_EUNSUPPORTED, "H-solve: R_x+R_d = %d needs %zu bytes of shared memory per CTA", d.R, sm);
+    if (sm > 48 * 1024) SN_CUDA(cudaFuncSetAttribute(hsolve_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    hsolve_stream_kernel<<<dim3(n_active), dim3(HG_THREADS), sm, ctx->stream>>>(d, sc, st, fr, h_init, g_step);
+    count_launch(ctx);
+    check_launch(ctx, "hsolve_stream_kernel");
+    return;
+  }
   SN_REQUIRE(d.R <= HS_THREADS, SNMFNAT_EUNSUPPORTED, "H-solve kernel supports R_x+R_d <= %d (got %d)", HS_THREADS, d.R);
   SN_REQUIRE((int)L.bytes <= ctx->max_smem_optin, SNMFNAT_EUNSUPPORTED,
              "basis slice (%zu bytes) does not fit the %d-byte shared memory of one CTA", L.bytes, ctx->max_smem_optin);

@@ -640,6 +640,7 @@ int snmfnat_train_reset(snmfnat_train* t) {
 
 int snmfnat_train_iterate(snmfnat_train* t, int n_iters, double* div, double* cost) {
   SN_API_BEGIN
+  NvtxRange nvtx_it("snmfnat_train_iterate");
   SN_REQUIRE(t != nullptr && n_iters >= 0, SNMFNAT_EINVAL, "bad argument");
   SN_CUDA(cudaSetDevice(t->ctx->device));
   const bool want = div || cost;

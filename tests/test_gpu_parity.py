@@ -139,6 +139,51 @@ def test_settings_variants(api, O, bases, wavs, rng_inputs, variant):
     assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1
 
 
+def _grow(B, cols, seed):
+    """A dictionary with `cols` columns made of perturbed copies of the shipped one (unit-free, non-negative)."""
+    rs = np.random.RandomState(seed)
+    reps = [B[:, rs.permutation(B.shape[1])] * np.exp(0.3 * rs.randn(*B.shape)) for _ in range((cols + B.shape[1] - 1) // B.shape[1])]
+    return np.concatenate([B] + reps, axis=1)[:, :cols].copy()
+
+
+@pytest.mark.parametrize("setting", ["techwin_R240_3classes", "exemplar_R1000"])
+def test_large_rank_settings_of_the_reference(api, O, bases, wavs, rng_inputs, setting):
+    """settings/bak_IS16_results/initial_setting_Proposed_Techwin_201603_RT.m:40-61 (R_x = 140 in three event classes,
+    R_d = 100, R_a = 25, overlap_m_a = 0.1, max_iter = 25) and initial_setting_Exemplar.m:47-58,104 (R_x = R_d = 500, no
+    adaptation, max_iter = 50): dictionaries that do not fit the cluster-resident H-solve run on the streaming kernel and
+    must still reproduce the oracle hop by hop."""
+    if setting.startswith("techwin"):
+        over = dict(EVENT_NUM=3, EVENT_RANK=[1, 21, 41], R_x=140, R_d=100, R_a=25, m_a=100, overlap_m_a=0.1, max_iter=25)
+        Bx, Bd = _grow(bases["B_DFT_x"], 140, 1), bases["B_DFT_d"]
+        hops = 70
+    else:
+        over = dict(R_x=500, R_d=500, R_a=50, m_a=40, overlap_m_a=0.5, adapt_train_N=0, max_iter=50)
+        Bx, Bd = _grow(bases["B_DFT_x"], 500, 2), _grow(bases["B_DFT_d"], 500, 3)
+        hops = 25
+    R = over["R_x"] + over["R_d"]
+    rs = np.random.RandomState(41)
+    h_init = O.park_miller(R, 1)
+    Ad = rs.rand(over["R_a"], over["m_a"])
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    pcms = [wavs["M03_in"][8000:8000 + 160 * hops], wavs["M04_in"][3000:3000 + 160 * (hops - 9) + 31]]
+    ctx = api.get_context(0)
+    b = api.Batch(ctx, p, Bx, Bd, [len(x) for x in pcms], h_init, np.stack([Ad, Ad]))
+    b.enable_trace(True)
+    b.upload(pcms)
+    b.run()
+    outs = b.download()
+    for i, pcm in enumerate(pcms):
+        tr = []
+        ref, _ = O.enhance_utterance(pcm, po, Bx, Bd, h_init=h_init, Ad_blk_init=Ad, trace=tr)
+        assert np.array_equal(b.trace(i, "h_iters").astype(int), np.array([t["h_iters"] for t in tr])), i
+        assert np.array_equal(b.trace(i, "w_iters").astype(int), np.array([t["w_iters"] for t in tr])), i
+        A = b.trace(i, "A")
+        assert max(rel_err(tr[k]["A"], A[k]) for k in range(len(tr))) <= SPEC_TOL
+        assert np.abs(outs[i].astype(int) - ref.astype(int)).max() <= 1, i
+    b.close()
+
+
 def test_chain_mode_carries_the_noise_basis_between_files(api, O, bases, wavs, rng_inputs):
     """Do_MultiBatch / NTF_sep_event_RT semantics (src/NTF_sep_event_RT.m:28-38,136-139): inside a target directory the
     adapted noise basis of file i is the starting basis of file i+1 (B_D_u.mat); chains are independent of each other
