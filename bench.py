@@ -225,7 +225,9 @@ def run_reference(args, rank, world):
             audio = a
     ms = 1e3 * float(np.mean(times))
     val = audio / (ms / 1e3)
-    sample = f"{cores} utterances x {crop:.0f} s of the same synthetic batch, one oracle process per core"
+    sample = (f"{cores} utterances x {crop:.0f} s crops of the same synthetic RECIPE (bench_workload.py, NumPy generator; the GPU arm "
+              f"synthesises its batch with the torch generator of the same recipe, so the waveforms differ), one float64 NumPy "
+              f"oracle process per core; 3 s crops over-weight the 15 noise-only initialisation frames")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup_ref, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -434,7 +436,7 @@ def run_ours(args, rank, world, local_rank):
     # launch, divided by the solves of that launch), scaled to the average number of solves per launch of this run
     traffic = None
     try:
-        tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+        tj = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text())
         per_solve = float(tj[dom]["dram_bytes_per_solve"])
         solves = {"hsolve": stats["hops"], "wsolve": stats["w_solves"]}.get(dom)
         if solves:
@@ -445,10 +447,13 @@ def run_ours(args, rank, world, local_rank):
         traffic = None
     roofline.update({"kernel": dom + "_kernel", "traffic": traffic,
                      "peak_source": pk["_fp64_source"] if roofline["unit"] == "TFLOP/s" else pk["_hbm_source"],
-                     "structural_ceiling": {
-                         "frac_of_peak": 0.25, "why": "both mat-vecs of an H-solve iteration read the FP64 basis slice from "
-                         "shared memory: 8 B per FMA at 128 B/clk/SM = 16 FMA/clk/SM against the pipe's 64; ncu "
-                         "(profiles/r01_v6_hsolve_fast_ncu_full.txt): the shared-memory pipe is 64 % busy"} if dom == "hsolve" else None,
+                     "what_bounds_it": {
+                         "hsolve": "multi-stream kernel (DESIGN.md 4.1): 3/4 of the flops as FP64 tensor-core tiles from registers, 1/4 "
+                                   "as shared-memory mat-vecs; the per-iteration exchange over distributed shared memory is 30 % of "
+                                   "an iteration (profiles/r02_hsolve_ms_probe.txt)",
+                         "wsolve": "the GEMM loop runs at 85-93 % of the FP64 pipe (profiles/r02_wsolve_probe.txt); the fraction "
+                                   "reported here divides ALGORITHMIC flops by the whole kernel time: padding 1.33x, rcp/log of the "
+                                   "ratio step 1.2x, one cost-only pass per solve, two exchanges per pass (DESIGN.md 4.2)"}.get(dom),
                      "note": "fp64 = FP64 FMA pipe (DFMA issue rate); tensor = FP64 tensor-core mma.sync m8n8k4 "
                              "(MEASURED_PEAKS.json holds no FP64 figure, so the FP64 peaks are measured by "
                              "tools/peaks_fp64); achieved = SURVEY.md 8(d) algorithmic flops / CUDA-event time"})

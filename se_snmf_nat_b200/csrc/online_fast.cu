@@ -496,7 +496,11 @@ struct WfLayout {
     NP = (m_a + 15) / 16 * 16;
     HSd = NP + ((2 - NP % 8) + 8) % 8;          // == 2 (mod 8): conflict-free fragment loads in both GEMMs
     VROWS = (TPC + 1) * 8;                      // local rows (leftover tile included)
-    VS = VROWS + 1;                             // odd stride: conflict-free (t, row) fragment reads
+    VS = VROWS + 1;                             // odd stride: conflict-free (t, row) fragment reads.  Tried in round 2 and
+                                                // measured slower on the same box (747 -> 771 ms per 1024 x 1.5 s): an even
+                                                // stride with one bulk copy per history column, and an 8-column tail tile
+                                                // (312 instead of 336 mma per pass: the extra code spills at the 96 registers a
+                                                // 17-warp CTA gets)
     size_t o = 0;
     off_H = o;       o += (size_t)KMAX * HSd;
     off_V = o;       o += VSMEM ? (size_t)NP * VS : 0;
@@ -942,11 +946,13 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
     if (left_warp) left_partial(0, [&](int r, int k) { return Wl[r * KMAX + k] * Wl[r * KMAX + k]; });
     else warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
     cluster_combine(1, false, nullptr, true);
-    if (left_warp)
+    if (left_warp) {
       for (int i = lane; i < nleft * KMAX; i += 32) {
         const int k = i % KMAX;
         if (k < Ru) Wl[i] = Wl[i] * tot[k];
       }
+      __syncwarp();   // the next pass reads every atom of the row from every lane
+    }
 #pragma unroll
     for (int j = 0; j < KT; ++j)
 #pragma unroll

@@ -64,10 +64,10 @@ struct MsLayout {
   static constexpr size_t off_recv = off_hS + 8 * MS_HLD;                      // [8][ROWLEN] partials of the owned stream
   static constexpr size_t off_lamp = off_recv + 8 * MS_ROWLEN;                 // [8][LLD] private part of Lambda
   static constexpr size_t off_rS = off_lamp + 8 * MS_LLD;                      // [8][RLD] ratio v./Lambda
-  static constexpr size_t off_costw = off_rS + 8 * MS_RLD;                     // [9][8] cost partials per warp (+ tail row)
-  static constexpr size_t off_WnS = off_costw + 72;                            // [KS] tail row of the shared columns
+  static constexpr size_t off_costw = off_rS + 8 * MS_RLD;                     // [8][8] cost partials per warp + [2][8] tail row
+  static constexpr size_t off_WnS = off_costw + 80;                            // [KS] tail row of the shared columns
   static constexpr size_t off_WnP = off_WnS + MS_KS;                           // [S][RA] tail row of the private columns
-  static constexpr size_t off_rN = off_WnP + (size_t)((S * MS_RA + 1) & ~1);   // [8] ratio of the tail row, [8] Lambda of it
+  static constexpr size_t off_rN = off_WnP + (size_t)((S * MS_RA + 1) & ~1);   // [2][8] ratio of the tail row (by parity)
   static constexpr size_t off_hsum = off_rN + 16;                              // [2][8]
   static constexpr size_t off_bar = off_hsum + 16;                             // 2 mbarriers
   static constexpr size_t off_slot = off_bar + 2;                              // 8 ints
@@ -329,7 +329,7 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   for (int i = tid; i < 8 * MS_HLD; i += MS_THREADS) hS[i] = 0.0;
   for (int i = tid; i < 8 * MS_RLD; i += MS_THREADS) rS[i] = 0.0;
   for (int i = tid; i < 8 * MS_LLD; i += MS_THREADS) lam_p[i] = 0.0;
-  if (tid < 72) costw[tid] = 0.0;
+  if (tid < 80) costw[tid] = 0.0;
   if (tid < 16) {
     rN[tid] = 0.0;
     hsumw[tid] = 0.0;
@@ -479,7 +479,12 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   };
 
   MS_TICK(10);
+  // The tail-row ratio / cost of iteration t are written in phase A and read in phase B; the writers of iteration t+1 are
+  // only released by the exchange (the owners need this CTA's partials first), which a race checker cannot see: the two
+  // small arrays are double-buffered by iteration parity so that the ordering is also visible inside the CTA.
+  int par = 0;
   for (;;) {
+    par ^= 1;
     hf_mbar_wait_bounded(barAG, parAG);
     MS_TICK(0);
     parAG ^= 1u;
@@ -514,8 +519,8 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
         ctn = fma(vN, fast_log(rn, log_tab), lam - vN);
       }
       if (lane == 0) {
-        rN[warp] = rn;
-        costw[64 + warp] = ctn;
+        rN[par * 8 + warp] = rn;
+        costw[64 + par * 8 + warp] = ctn;
       }
     }
     MS_TICK(1);
@@ -553,7 +558,7 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
         const int n = 2 * lj + e;
         if (n < S) {
           const unsigned ra = hf_mapa(la, (unsigned)n), rbar = hf_mapa(barRS, (unsigned)n);
-          const double rn = tail_rank ? rN[n] : 0.0;
+          const double rn = tail_rank ? rN[par * 8 + n] : 0.0;
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             if (q == 2 && !nt3) break;
@@ -565,8 +570,8 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
       }
       if (warp < S) {
         if (tail_rank) {
-          ga = fma(WnP[warp * MS_RA + a0], rN[warp], ga);
-          gb = fma(WnP[warp * MS_RA + a1c], rN[warp], gb);
+          ga = fma(WnP[warp * MS_RA + a0], rN[par * 8 + warp], ga);
+          gb = fma(WnP[warp * MS_RA + a1c], rN[par * 8 + warp], gb);
         }
         push_partial(warp, MS_PRIV0 + a0, ga);
         if (has1) push_partial(warp, MS_PRIV0 + a1, gb);
@@ -576,7 +581,8 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
         if (lane < S) {
           double s = 0.0;
 #pragma unroll
-          for (int w = 0; w < 9; ++w) s += costw[w * 8 + lane];
+          for (int w = 0; w < 8; ++w) s += costw[w * 8 + lane];
+          s += costw[64 + par * 8 + lane];
           push_partial(lane, MS_FLAG, s);
         }
       }
