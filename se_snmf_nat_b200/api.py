@@ -648,15 +648,20 @@ class StreamState:
                "lambda_dav": ("F",), "Xm_tilde": ("F",), "Ym": ("F",), "Yp": ("F",), "A": ("R",), "Q": ("F",),
                "G": ("F",), "Xm_hat": ("F",), "Dm_hat": ("F",), "update_switch": (1,), "stats": (5,)}
 
-    def __init__(self, ctx: Context, handle, ps: Params):
+    def __init__(self, ctx: Context, handle, ps: Params, n1=None):
         self.ctx, self._h, self._ps = ctx, handle, ps
         self._dims = {"F": ps.fftlength // 2 + 1, "R_x": ps.R_x, "R_d": ps.R_d, "R": ps.R_x + ps.R_d, "R_a": ps.R_a,
                       "m_a": ps.m_a, "P_len_l": ps.P_len_l}
+        # B_sep_mode = 'Mel': the Mel dictionaries and the Mel image of the noise history have n1 rows
+        self._mel_rows = int(n1) if (ps.B_sep_mode == _lib.SEP_MEL and n1) else None
 
     def _shape(self, name):
         if name not in self._SHAPES:
             raise KeyError(name)
-        return tuple(self._dims.get(x, x) for x in self._SHAPES[name])
+        shp = tuple(self._dims.get(x, x) for x in self._SHAPES[name])
+        if self._mel_rows and name in ("B_Mel_d", "B_Mel_x", "lambda_d_blk"):
+            shp = (self._mel_rows,) + shp[1:]
+        return shp
 
     def __getitem__(self, name):
         shp = self._shape(name)
@@ -695,7 +700,7 @@ def init_buff(B_Mel_x, B_Mel_d, B_DFT_x, B_DFT_d, p: dict, *, Ad_blk_init, A_d_i
     check(ctx._lib.snmfnat_stream_create(ctx._h, C.byref(ps), _dptr(win_s), _dptr(win_i), _dptr(Bmx), _dptr(Bmd),
                                          Bmd.shape[0], _dptr(Bx), _dptr(Bd), Bx.shape[0], _dptr(ad), _dptr(a_d),
                                          C.byref(h)))
-    return StreamState(ctx, h, ps)
+    return StreamState(ctx, h, ps, n1=Bmd.shape[0])
 
 
 def bnmf_sep_event_RT_IS16(y, l, g: StreamState, p: dict, *, h_init, nargout: int = 3):

@@ -14,6 +14,7 @@ struct snmfnat_stream {
   Config cfg;
   SlotBuffers sb;
   DevBuf<double> y, frame, Ym, Yp, Xt, cls, xt_host_dev;
+  DevBuf<double> Ysep;   // Mel mode: the separation input of the current frame [LD1]
   DevBuf<double2> Yc;
   FftPlans fft;
   int last_l = 0;
@@ -84,20 +85,34 @@ int snmfnat_stream_create(snmfnat_ctx* ctx, const snmfnat_params* p, const doubl
   s->ctx = ctx;
   make_config(ctx, *p, n2, s->cfg);
   const Config& c = s->cfg;
-  SN_REQUIRE(!c.sc.mel_mode, SNMFNAT_EUNSUPPORTED,
-             "B_sep_mode='Mel' is available through the batch entry (snmfnat_batch_set_mel), not the per-hop stream entry");
-  SN_REQUIRE(n1 == n2, SNMFNAT_EUNSUPPORTED, "DFT mode expects the Mel slots to hold the DFT bases (n1 == n2)");
+  const bool mel = c.sc.mel_mode != 0;
+  if (mel) {
+    // B_sep_mode = 'Mel' (filewise_run_IS16.m:46-51): separation and adaptation on the n1-band Mel dictionaries, gain and
+    // block sparsity in the DFT domain (bnmf_sep_event_RT_IS16.m:107-119,165-211,295-319), as in the batch entry
+    SN_REQUIRE(B_Mel_x && B_Mel_d && n1 > 0 && n1 <= 256, SNMFNAT_EINVAL, "Mel mode needs B_Mel_x / B_Mel_d (n1 <= 256 bands)");
+    SN_REQUIRE(c.p.MelConv != 0, SNMFNAT_EUNSUPPORTED, "Mel mode with MelConv = 0 is not supported");
+    SN_REQUIRE(c.p.F_order == n1, SNMFNAT_EINVAL, "B_Mel has %d rows but p.F_order = %d", n1, c.p.F_order);
+    SN_REQUIRE(c.p.EVENT_NUM == 1 && c.p.NOISE_NUM == 1, SNMFNAT_EUNSUPPORTED,
+               "Mel mode through the per-hop entry supports one event and one noise class");
+  } else {
+    SN_REQUIRE(n1 == n2, SNMFNAT_EUNSUPPORTED, "DFT mode expects the Mel slots to hold the DFT bases (n1 == n2)");
+  }
   s->sb.alloc(1, c.d);
   // B_DFT_d is the adaptable basis; the "B_Mel_d" slot supplies the never-updated columns (:328 [sic])
-  s->sb.set_bases(ctx, B_DFT_x, B_Mel_d ? B_Mel_d : B_DFT_d);
-  (void)B_Mel_x;
+  s->sb.set_bases(ctx, B_DFT_x, (!mel && B_Mel_d) ? B_Mel_d : B_DFT_d);
+  if (mel) {
+    std::vector<double> M((size_t)c.d.F * n1);
+    mel_matrix_host(c.p.fs, n1, c.p.fftlength, 1.0, c.p.fs / 2.0, M.data());     // init_buff.m:60-62
+    s->sb.set_mel(ctx, n1, B_Mel_x, B_Mel_d, M.data());
+    s->Ysep.alloc(s->sb.LD1);
+  }
   std::vector<int> order(1, 0);
   if (c.sc.adapt_train_N) s->sb.set_ad_init(ctx, Ad_blk_init, 0, 1, order);
   s->sb.win_stft.alloc(c.g.sz); s->sb.win_istft.alloc(c.g.sz);
   SN_CUDA(cudaMemcpy(s->sb.win_stft.p, win_stft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
   SN_CUDA(cudaMemcpy(s->sb.win_istft.p, win_istft, c.g.sz * sizeof(double), cudaMemcpyHostToDevice));
   s->sb.reset(ctx);
-  if (B_Mel_d && B_Mel_d != B_DFT_d) {
+  if (!mel && B_Mel_d && B_Mel_d != B_DFT_d) {
     // The adaptable atoms (columns < R_a) start from B_DFT_d; the never-updated ones stay B_Mel_d(:, R_a+1:end) in BOTH
     // ping-pong buffers: the reference re-assembles [B_rem, B_new, B_Mel_d(:, R_a+1:end)] on every update (:328,336), so
     // from the first update on the fixed columns are B_Mel_d's whatever B_DFT_d held there.  Before the first update the
@@ -165,12 +180,31 @@ int snmfnat_stream_step(snmfnat_stream* s, const double* y, int l, const double*
   // separation, gain, adaptation (:104-347)
   const SlotState sv = s->sb.view();
   FrameArrays fr{s->Ym.p, s->Xt.p};
-  launch_hsolve(ctx, c.d, c.sc, sv, fr, s->sb.h_init.p, 1, 0);
-  launch_gain(ctx, c.d, c.sc, sv, fr, nullptr, 1, 0);
-  launch_wsolve(ctx, c.d, c.sc, sv, nullptr, 1, 0);
+  if (!c.sc.mel_mode) {
+    launch_hsolve(ctx, c.d, c.sc, sv, fr, s->sb.h_init.p, 1, 0);
+    launch_gain(ctx, c.d, c.sc, sv, fr, nullptr, 1, 0);
+    launch_wsolve(ctx, c.d, c.sc, sv, nullptr, 1, 0);
+  } else {
+    const SlotState sm = s->sb.view_mel();
+    const OnlineDims dm = s->sb.dims_mel();
+    FrameArrays frm{s->Ysep.p, nullptr};
+    launch_mel_project(ctx, s->sb.melM.p, s->sb.n1, s->sb.LD1, c.d.F, c.d.LDF, s->Ym.p, 1, s->Ysep.p);
+    launch_hsolve(ctx, dm, c.sc, sm, frm, s->sb.h_init.p, 1, 0);
+    launch_mel_post(ctx, c.d, sv, s->sb.melM.p, s->sb.n1, s->sb.LD1, s->sb.XhatM.p, s->sb.DhatM.p, s->Ysep.p, 1, 0);
+    launch_gain(ctx, c.d, c.sc, sv, fr, nullptr, 1, 0);
+    if (c.sc.adapt_train_N) {
+      launch_mel_hist(ctx, c.d, sv, s->sb.melM.p, s->sb.n1, s->sb.LD1, s->sb.lam_blk_mel.p, 1, 0);
+      launch_wsolve(ctx, dm, c.sc, sm, nullptr, 1, 0);
+    }
+  }
   // ISTFT (:349-363)
   istft_one(s, s->Xt.p, x_tilde);
-  if (x_hat_i || d_hat_i) {
+  if ((x_hat_i || d_hat_i) && c.sc.mel_mode) {
+    // one event / one noise class: the class reconstructions are melmat' * (B_Mel * A) = what mel_post_kernel left in
+    // Xhat / Dhat (bnmf_sep_event_RT_IS16.m:165-202)
+    if (x_hat_i) istft_one(s, s->sb.Xhat.p, x_hat_i);
+    if (d_hat_i) istft_one(s, s->sb.Dhat.p, d_hat_i);
+  } else if (x_hat_i || d_hat_i) {
     const snmfnat_params& p = c.p;
     std::vector<int> lo, hi;
     for (int i = 0; i < p.EVENT_NUM; ++i) {   // :159-164
@@ -249,7 +283,23 @@ int snmfnat_stream_get(snmfnat_stream* s, const char* field, double* buf, int64_
     SN_CUDA(cudaMemcpy(&v, dev, sizeof(int), cudaMemcpyDeviceToHost));
     buf[0] = v;
   };
-  if (f == "B_DFT_d") { need((int64_t)d.F * d.R_d); download_basis(ctx, current_bd(s), d.F, d.R_d, d.LDF, buf); }
+  const bool mel = c.sc.mel_mode != 0;
+  const int n1 = s->sb.n1, LD1 = s->sb.LD1;
+  if (mel && f == "B_Mel_d") {          // the adapted dictionary of Mel mode (n1 x R_d)
+    need((int64_t)n1 * d.R_d);
+    int sel = 0;
+    SN_CUDA(cudaMemcpy(&sel, s->sb.bd_sel.p, sizeof(int), cudaMemcpyDeviceToHost));
+    download_basis(ctx, sel ? s->sb.BdM1.p : s->sb.BdM0.p, n1, d.R_d, LD1, buf);
+  } else if (mel && f == "B_Mel_x") {
+    need((int64_t)n1 * d.R_x);
+    download_basis(ctx, s->sb.BxM.p, n1, d.R_x, LD1, buf);
+  } else if (mel && f == "lambda_d_blk") {   // Mel image of the noise-spectrum history (:295-301), n1 x m_a
+    need((int64_t)n1 * d.m_a);
+    int head = 0;
+    SN_CUDA(cudaMemcpy(&head, s->sb.ring_head.p, sizeof(int), cudaMemcpyDeviceToHost));
+    ring_get(ctx, s->sb.lam_blk_mel.p, LD1, n1, d.m_a, head, buf);
+  }
+  else if (f == "B_DFT_d") { need((int64_t)d.F * d.R_d); download_basis(ctx, mel ? s->sb.Bd_fix.p : current_bd(s), d.F, d.R_d, d.LDF, buf); }
   else if (f == "B_Mel_d") { need((int64_t)d.F * d.R_d); download_basis(ctx, s->sb.Bd_fix.p, d.F, d.R_d, d.LDF, buf); }
   else if (f == "B_DFT_x" || f == "B_Mel_x") { need((int64_t)d.F * d.R_x); download_basis(ctx, s->sb.Bx.p, d.F, d.R_x, d.LDF, buf); }
   else if (f == "Ad_blk") {

@@ -323,3 +323,34 @@ def test_stream_fixed_columns_follow_the_mel_slot_after_updates(api, O, bases, w
     assert rel_err(go.B_DFT_d, g["B_DFT_d"]) < 1e-9
     assert rel_err(Bmel[:, 50:], g["B_DFT_d"][:, 50:]) < 1e-12
     g.close()
+
+
+def test_per_hop_stream_mel_mode(api, O, bases, wavs, rng_inputs):
+    """p.B_sep_mode = 'Mel' through init_buff + bnmf_sep_event_RT_IS16 hop by hop (the latency entry): separation and
+    adaptation on the 64-band Mel dictionaries, everything else in the DFT domain, exactly like the batch entry."""
+    h_init, Ad = rng_inputs
+    over = dict(B_sep_mode="Mel", MelConv=1)
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    Bx, Bd, Bmx, Bmd = bases["B_DFT_x"], bases["B_DFT_d"], bases["B_Mel_x"], bases["B_Mel_d"]
+    g = api.init_buff(Bmx, Bmd, Bx, Bd, p, Ad_blk_init=Ad)
+    go = O.init_buff(Bmx, Bmd, Bx, Bd, po, Ad_blk_init=Ad)
+    pcm = wavs["M03_in"][6000:6000 + 160 * 70]
+    y = np.zeros(640)
+    updates = 0
+    for l in range(1, 71):
+        y = np.concatenate([y[160:], pcm[(l - 1) * 160:l * 160].astype(float)])
+        aux = l in (20, 50)
+        xh, dh, xt, g = api.bnmf_sep_event_RT_IS16(y, l, g, p, h_init=h_init, nargout=3 if aux else 1)
+        xho, dho, xto, go = O.bnmf_sep_event_RT_IS16(y, l, go, po, h_init=h_init, want_aux=aux)
+        updates += int(go.dbg["w_iters"] > 0)
+        st = g["stats"]
+        assert int(st[0]) == go.dbg["h_iters"] and int(st[3]) == go.dbg["w_iters"], l
+        assert np.max(np.abs(xt - xto)) <= 1e-6 * max(1.0, np.max(np.abs(xto))), l
+        if aux:
+            assert np.max(np.abs(xh[0, 0] - xho[0])) <= 1e-6 * max(1.0, np.max(np.abs(xho)))
+            assert np.max(np.abs(dh[0, 0] - dho[0])) <= 1e-6 * max(1.0, np.max(np.abs(dho)))
+    assert updates > 0
+    assert g["B_Mel_d"].shape == (64, 100) and rel_err(go.B_Mel_d, g["B_Mel_d"]) < 1e-9
+    assert rel_err(go.lambda_d_blk, g["lambda_d_blk"]) < 1e-9
+    g.close()
