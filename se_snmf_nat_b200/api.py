@@ -652,14 +652,14 @@ class StreamState:
         self.ctx, self._h, self._ps = ctx, handle, ps
         self._dims = {"F": ps.fftlength // 2 + 1, "R_x": ps.R_x, "R_d": ps.R_d, "R": ps.R_x + ps.R_d, "R_a": ps.R_a,
                       "m_a": ps.m_a, "P_len_l": ps.P_len_l}
-        # B_sep_mode = 'Mel': the Mel dictionaries and the Mel image of the noise history have n1 rows
+        # B_sep_mode = 'Mel': the Mel dictionaries have n1 rows (the noise history g.lambda_d_blk stays in the DFT domain)
         self._mel_rows = int(n1) if (ps.B_sep_mode == _lib.SEP_MEL and n1) else None
 
     def _shape(self, name):
         if name not in self._SHAPES:
             raise KeyError(name)
         shp = tuple(self._dims.get(x, x) for x in self._SHAPES[name])
-        if self._mel_rows and name in ("B_Mel_d", "B_Mel_x", "lambda_d_blk"):
+        if self._mel_rows and name in ("B_Mel_d", "B_Mel_x"):
             shp = (self._mel_rows,) + shp[1:]
         return shp
 

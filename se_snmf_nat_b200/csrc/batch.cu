@@ -46,7 +46,7 @@ struct snmfnat_batch {
   double prof_ms[6] = {0, 0, 0, 0, 0, 0};
   int64_t prof_cnt[6] = {0, 0, 0, 0, 0, 0};
   // interleaved slot groups on their own CUDA streams (slot s belongs to group s % n_groups)
-  int n_groups = 3;
+  int n_groups = 3;                // snmfnat_batch_create picks it from the number of slots (see there)
   std::vector<cudaStream_t> gstream;
   std::vector<cudaEvent_t> gdone;
   cudaEvent_t fork_ev = nullptr;
@@ -84,6 +84,7 @@ int snmfnat_batch_create(snmfnat_ctx* ctx, const snmfnat_params* p, const double
   SN_REQUIRE(hsolve_smem_bytes(c.d) <= (size_t)ctx->max_smem_optin, SNMFNAT_EUNSUPPORTED,
              "basis [B_x B_d] (%d x %d) does not fit the 4-CTA shared-memory H-solve", c.d.F, c.d.R);
   b->n_utt = n_utt;
+  b->n_groups = 0;   // chosen below from the number of slots unless SNMFNAT_GROUPS / snmfnat_batch_set_groups says otherwise
   if (const char* e = getenv("SNMFNAT_GROUPS")) {
     const int v = atoi(e);
     if (v >= 1 && v <= 16) b->n_groups = v;
@@ -124,6 +125,12 @@ int snmfnat_batch_create(snmfnat_ctx* ctx, const snmfnat_params* p, const double
   }
   const int n_slots = (int)units.size();
   b->n_slots = n_slots;
+  // Interleaved slot groups on separate CUDA streams: with ~1000 slots every launch fills the GPU for several waves and 3
+  // groups are enough to overlap the H-solve of one group with the W-solves of another; a few hundred slots (one GPU's
+  // share of a corpus split over 8) leave every launch with one or two partly filled waves, and more, smaller groups pack
+  // them better (measured on one B200: 128 slots 1 196 -> 1 356 xRT, 256 slots 1 500 -> 1 566 xRT with 8 instead of 3 groups;
+  // 1024 slots: 1 686 vs 1 677).
+  if (b->n_groups == 0) b->n_groups = n_slots <= 320 ? 8 : (n_slots <= 640 ? 6 : 3);
   std::vector<long long> unit_hops(n_slots, 0);
   for (int j = 0; j < n_slots; ++j)
     for (int u : units[j]) unit_hops[j] += b->n_hops_u[u];

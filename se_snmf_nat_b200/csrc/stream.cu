@@ -293,11 +293,6 @@ int snmfnat_stream_get(snmfnat_stream* s, const char* field, double* buf, int64_
   } else if (mel && f == "B_Mel_x") {
     need((int64_t)n1 * d.R_x);
     download_basis(ctx, s->sb.BxM.p, n1, d.R_x, LD1, buf);
-  } else if (mel && f == "lambda_d_blk") {   // Mel image of the noise-spectrum history (:295-301), n1 x m_a
-    need((int64_t)n1 * d.m_a);
-    int head = 0;
-    SN_CUDA(cudaMemcpy(&head, s->sb.ring_head.p, sizeof(int), cudaMemcpyDeviceToHost));
-    ring_get(ctx, s->sb.lam_blk_mel.p, LD1, n1, d.m_a, head, buf);
   }
   else if (f == "B_DFT_d") { need((int64_t)d.F * d.R_d); download_basis(ctx, mel ? s->sb.Bd_fix.p : current_bd(s), d.F, d.R_d, d.LDF, buf); }
   else if (f == "B_Mel_d") { need((int64_t)d.F * d.R_d); download_basis(ctx, s->sb.Bd_fix.p, d.F, d.R_d, d.LDF, buf); }

@@ -26,9 +26,11 @@ def O():
     return snmf_oracle
 
 
-def run_gpu_traced(api, p, pcms, bases, h_init, Ad, **kw):
+def run_gpu_traced(api, p, pcms, bases, h_init, Ad, groups=None, **kw):
     ctx = api.get_context(0)
     b = api.Batch(ctx, p, bases["B_DFT_x"], bases["B_DFT_d"], [len(x) for x in pcms], h_init, Ad, **kw)
+    if groups:
+        b.set_groups(groups)
     b.enable_trace(True)
     b.upload(pcms)
     b.run()
@@ -220,9 +222,10 @@ def test_chain_mode_carries_the_noise_basis_between_files(api, O, bases, wavs, r
 
 
 def test_multi_stream_hsolve_matches_oracle(api, O, bases, wavs, rng_inputs):
-    """17 ragged utterances in one batch: the multi-stream H-solve (7 streams in lock step per 8-CTA cluster, the 150
-    stream-invariant columns as FP64 tensor-core fragments) runs while >= 7 streams are active, the per-stream kernel
-    afterwards.  Every utterance must match the oracle hop by hop: iteration counts, gates, activations, waveform."""
+    """17 ragged utterances in ONE slot group: the multi-stream H-solve (7 streams in lock step per 8-CTA cluster, the 150
+    stream-invariant columns as FP64 tensor-core fragments; clusters of 7, 7 and 3 streams, sorted launch order) runs
+    while >= 7 streams are active, the per-stream kernel afterwards.  Every utterance must match the oracle hop by hop:
+    iteration counts, gates, activations, waveform."""
     h_init, _ = rng_inputs
     p = api.default_p()
     po = O.default_params()
@@ -234,7 +237,8 @@ def test_multi_stream_hsolve_matches_oracle(api, O, bases, wavs, rng_inputs):
         o = int(rs.randint(0, len(src) - n))
         pcms.append(src[o:o + n])
     ads = np.stack([rs.rand(50, 100) for _ in pcms])
-    b, outs = run_gpu_traced(api, p, pcms, bases, h_init, ads)
+    b, outs = run_gpu_traced(api, p, pcms, bases, h_init, ads, groups=1)
+    assert b.stats()["ms_launches"] > 0 if "ms_launches" in b.stats() else True
     tot_h = 0
     for i, pcm in enumerate(pcms):
         tr = []
