@@ -338,6 +338,25 @@ def enhance_batch_multi(pcms: Sequence[np.ndarray], p: dict, B_x, B_d, *, h_init
     return outs
 
 
+def save_basis_mat(path: str, B_DFT_sub, B_Mel_sub, A_DFT_sub=None, A_Mel_sub=None):
+    """run_basis_train.m:136 saves 'B_DFT_sub', 'B_Mel_sub', 'A_DFT_sub', 'A_Mel_sub' with '-v7.3' (HDF5).  This writes the
+    same four variables as MAT v5, which the reference's own loader (`load(...)`, run_basis_train.m:138, filewise_run_IS16.m:24-37)
+    reads just the same: `load` detects the version.  (HDF5 is not available in this environment; v5 caps a variable at
+    2 GB, enough for the dictionaries and for the activations of ~2.6 M frames at R = 100.)"""
+    import scipy.io
+    d = {"B_DFT_sub": _f64(B_DFT_sub), "B_Mel_sub": _f64(B_Mel_sub)}
+    d["A_DFT_sub"] = np.zeros((1, 1)) if A_DFT_sub is None else _f64(A_DFT_sub)      # run_basis_train.m:96-97: 0 when unused
+    d["A_Mel_sub"] = np.zeros((1, 1)) if A_Mel_sub is None else _f64(A_Mel_sub)
+    scipy.io.savemat(path, d, format="5", do_compression=False)
+
+
+def load_basis_mat(path: str) -> dict:
+    """The variables of a basis/*/R_<n>.mat file (MAT v5 / v7 as shipped by the reference)."""
+    import scipy.io
+    m = scipy.io.loadmat(path)
+    return {k: np.asarray(v, dtype=np.float64) for k, v in m.items() if not k.startswith("__")}
+
+
 def pcm2wav_samples(pcm: np.ndarray) -> np.ndarray:
     """src/pcm2wav.m:9-10: the raw int16 output is divided by 32767 and written with wavwrite(..., 16, ...), which
     quantises as round(x * 32768) (half away from zero) clipped to [-32768, 32767]: samples above 16383 in magnitude

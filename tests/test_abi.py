@@ -94,3 +94,18 @@ def test_pcm2wav_requantisation():
     s = np.array([0, 1, -1, 100, 16383, 16384, -16384, 20000, -20000, 32766, 32767, -32767, -32768], dtype=np.int16)
     want = [0, 1, -1, 100, 16383, 16385, -16385, 20001, -20001, 32767, 32767, -32768, -32768]
     assert api.pcm2wav_samples(s).tolist() == want
+
+
+def test_basis_mat_round_trip(tmp_path, bases):
+    """run_basis_train.m:136-138: the four variables a training run saves load back unchanged, and in the layout the
+    reference's shipped basis files have (B_DFT_sub 513 x R, B_Mel_sub 64 x R)."""
+    import numpy as np
+    from se_snmf_nat_b200 import api
+    f = tmp_path / "R_100.mat"
+    A = np.random.RandomState(0).rand(100, 37)
+    api.save_basis_mat(str(f), bases["B_DFT_x"], bases["B_Mel_x"], A, None)
+    m = api.load_basis_mat(str(f))
+    assert set(m) == {"B_DFT_sub", "B_Mel_sub", "A_DFT_sub", "A_Mel_sub"}
+    assert np.array_equal(m["B_DFT_sub"], bases["B_DFT_x"]) and np.array_equal(m["B_Mel_sub"], bases["B_Mel_x"])
+    assert np.array_equal(m["A_DFT_sub"], A) and m["A_Mel_sub"].shape == (1, 1)
+    assert f.read_bytes()[:19] == b"MATLAB 5.0 MAT-file"
