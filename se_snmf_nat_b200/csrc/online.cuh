@@ -75,6 +75,11 @@ struct SlotState {
   int* ms_perm_step = nullptr;
   int* ms_ticket = nullptr;
   int ms_perm_stride = 0;
+  // launch order of THIS hop's W-solve, written by the same CTA: gated slots first, longest expected solve first (passes of
+  // the slot's previous solve x atom tiles of this one), so that the launch does not end in a tail of a few long solves
+  int* ws_perm = nullptr;        // [16][ms_perm_stride]
+  int* ws_perm_step = nullptr;   // [16] the step it is valid for
+  int* w_last = nullptr;         // [S] passes of the slot's last W-solve
 };
 
 // Per-frame arrays shared by the STFT, the solvers and the ISTFT.

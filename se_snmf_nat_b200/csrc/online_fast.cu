@@ -561,7 +561,13 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   constexpr int THREADS = WARPS * 32;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int slot = d.slot0 + (int)(blockIdx.x / CL) * d.slot_stride;
+  // launch order written by this hop's gain kernel (gated slots first, longest expected solve first), if any
+  int idx = (int)(blockIdx.x / CL);
+  {
+    const int pg = d.slot0 & 15;
+    if (st.ws_perm && d.slot0 < 16 && st.ws_perm_step[pg] == g_step) idx = st.ws_perm[(size_t)pg * st.ms_perm_stride + idx];
+  }
+  const int slot = d.slot0 + idx * d.slot_stride;
   const int l = g_step + 1 - st.l_offset[slot];
   if (l < 1 || l > st.n_hops[slot]) return;
   if (!st.do_update[slot]) return;  // uniform over the cluster

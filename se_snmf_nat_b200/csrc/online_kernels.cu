@@ -487,6 +487,30 @@ __device__ void gain_order_next(const OnlineDims& d, const SlotState& st, int g_
   __syncthreads();
   int* perm = st.ms_perm + (size_t)grp * st.ms_perm_stride;
   for (int i = tid; i < n; i += blockDim.x) perm[atomicAdd(&base[key_of(i)], 1)] = i;
+  // the W-solve of THIS hop (launched next on the same stream): gated slots by expected length, the others last
+  if (st.ws_perm && st.w_last) {
+    __syncthreads();
+    for (int k = tid; k < 256; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    auto key_w = [&](int i) {
+      const int slot = d.slot0 + i * d.slot_stride;
+      if (!st.do_update[slot]) return 0;
+      const int kt = (st.n_up[slot] + 7) / 8, passes = st.w_last[slot] > 0 ? st.w_last[slot] + 1 : 6;
+      const int k = passes * kt;
+      return 1 + (k > 254 ? 254 : k);
+    };
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[key_w(i)], 1);
+    __syncthreads();
+    for (int k = tid; k < 256; k += blockDim.x) {
+      int b = 0;
+      for (int j = k + 1; j < 256; ++j) b += hist[j];
+      base[k] = b;
+    }
+    __syncthreads();
+    int* pw = st.ws_perm + (size_t)grp * st.ms_perm_stride;
+    for (int i = tid; i < n; i += blockDim.x) pw[atomicAdd(&base[key_w(i)], 1)] = i;
+    if (tid == 0) st.ws_perm_step[grp] = g_step;
+  }
   if (tid == 0) {
     st.ms_ticket[grp] = 0;
     st.ms_perm_step[grp] = g_step + 1;
@@ -633,6 +657,7 @@ gain_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, TraceA
   }
   if (tid == 0) {
     st.gated[slot] = gated ? 1 : 0;
+    if (st.w_last && st.w_iters[slot] > 0) st.w_last[slot] = st.w_iters[slot];   // kept for the W-solve launch order
     st.w_iters[slot] = 0;
     atomicAdd(&st.stats[0], 1ull);
     atomicAdd(&st.stats[1], (unsigned long long)st.h_iters[slot]);

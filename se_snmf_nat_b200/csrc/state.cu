@@ -93,6 +93,9 @@ void SlotBuffers::set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B
     ms_perm.alloc((size_t)16 * S);
     ms_perm_step.alloc(16);
     ms_ticket.alloc(16);
+    ws_perm.alloc((size_t)16 * S);
+    ws_perm_step.alloc(16);
+    w_last.alloc(S);
     launch_ms_colstat(ctx, d, Bx.p, Bd_fix.p, ms_colstat.p);
     SN_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -217,6 +220,8 @@ void SlotBuffers::reset(snmfnat_ctx* ctx) {
   if (ms_perm.n) {
     ms_ticket.zero(st);
     SN_CUDA(cudaMemsetAsync(ms_perm_step.p, 0xff, 16 * sizeof(int), st));   // -1: no order computed yet
+    SN_CUDA(cudaMemsetAsync(ws_perm_step.p, 0xff, 16 * sizeof(int), st));
+    w_last.zero(st);
   }
   fill_int_kernel<<<(S + 255) / 256, 256, 0, st>>>(update_switch.p, S, 1);  // init_buff.m:41
   count_launch(ctx);
@@ -259,6 +264,7 @@ SlotState SlotBuffers::view() const {
   v.stats = stats.p;
   v.ms_colstat = ms_colstat.p;
   v.ms_perm = ms_perm.p; v.ms_perm_step = ms_perm_step.p; v.ms_ticket = ms_ticket.p; v.ms_perm_stride = S;
+  v.ws_perm = ws_perm.p; v.ws_perm_step = ws_perm_step.p; v.w_last = w_last.p;
   return v;
 }
 
