@@ -131,13 +131,9 @@ __device__ __forceinline__ void ms_pass_a(const double (&Wa)[2 * MS_KT], unsigne
         const bool is_x = 2 * lj < MS_XR;
         if ((MODE == 1) != is_x) hh = make_double2(0.0, 0.0);
       }
-      if (u & 1) {
-        dmma884(q0, q1, Wa[2 * u], hh.x);
-        dmma884(q0, q1, Wa[2 * u + 1], hh.y);
-      } else {
-        dmma884(p0, p1, Wa[2 * u], hh.x);
-        dmma884(p0, p1, Wa[2 * u + 1], hh.y);
-      }
+      // two accumulator chains, alternating: consecutive mma never depend on each other (26 clk dependent latency)
+      dmma884(p0, p1, Wa[2 * u], hh.x);
+      dmma884(q0, q1, Wa[2 * u + 1], hh.y);
     }
     if (PRIV) {
 #pragma unroll
