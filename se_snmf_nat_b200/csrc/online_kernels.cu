@@ -401,6 +401,8 @@ int hsolve_ms_mode() {
   static int v = -2;
   if (v == -2) {
     const char* e = getenv("SNMFNAT_HSOLVE");
+    // "ms" forces the multi-stream kernel for any number of streams, "single" disables it; "ms7" (read in online_ms.cu)
+    // selects its all-shared-memory 7-stream variant instead of the 8-stream one with tensor memory
     v = !e ? 0 : (std::string(e) == "ms" ? 1 : (std::string(e) == "single" ? -1 : 0));
   }
   return v;

@@ -16,11 +16,19 @@
 //     h ./ wn + its done flag back to all 8 CTAs with one bulk copy each.  Streams that stopped keep their h; the cluster
 //     leaves the loop when all S are done, then one more pass gives B_x A_x and B_d A_d (bnmf_sep_event_RT_IS16.m:174,197).
 // Results per stream do not depend on which streams share a cluster.
+//
+// Where the private columns live (template <S, TS>): the first S - TS streams in shared memory as described; the last TS
+// (one per TMEM lane quadrant, TS <= 4) in TENSOR MEMORY, lane-private, in BOTH access patterns (row pair x atoms: 200
+// columns; atom x row pairs for the lane's two atoms: 256 columns), read with tcgen05.ld.32x32b by the warp that owns the
+// quadrant.  Tensor memory is otherwise idle in this kernel, delivers ~57 B/clk per quadrant next to the 128 B/clk of
+// shared memory (tools/tmem_probe.cu), and frees enough shared memory for the eighth stream: <8, 4> fills the N dimension
+// of the mma and halves the shared-memory traffic of the mat-vecs; <7, 0> is the all-shared-memory variant.
 #include <cooperative_groups.h>
 #include <cmath>
 #include <cstdlib>
 #include "online.cuh"
 #include "online_dev.cuh"
+#include "umma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -57,10 +65,15 @@ __device__ unsigned long long g_ms_probe[16];
 #define MS_TICK(i) do {} while (0)
 #endif
 
-template <int S>
+constexpr int MS_TM_A = 0;                 // TMEM columns of pattern A: 4 k .. 4 k + 3 = W[2 lane .. +1][k] (two doubles)
+constexpr int MS_TM_B = 4 * MS_RA;         // pattern B: MS_TM_B + 8 p .. + 7 = W[2p .. +1][lane], W[2p .. +1][32 + lane]
+static_assert(MS_TM_B + 8 * (MS_ROWS / 2) <= 512, "both patterns of a stream must fit the 512 columns of a quadrant");
+
+template <int S, int TS>
 struct MsLayout {
-  static constexpr size_t off_Wp = 0;                                          // [S][RA][64] swizzled private columns
-  static constexpr size_t off_hS = off_Wp + (size_t)S * MS_RA * MS_ROWS;       // [8][HLD]  h./wn per stream (+ done flag)
+  static constexpr int SS = S - TS;                                            // streams whose private columns are in shared memory
+  static constexpr size_t off_Wp = 0;                                          // [SS][RA][64] swizzled private columns
+  static constexpr size_t off_hS = off_Wp + (size_t)SS * MS_RA * MS_ROWS;      // [8][HLD]  h./wn per stream (+ done flag)
   static constexpr size_t off_recv = off_hS + 8 * MS_HLD;                      // [8][ROWLEN] partials of the owned stream
   static constexpr size_t off_lamp = off_recv + 8 * MS_ROWLEN;                 // [8][LLD] private part of Lambda
   static constexpr size_t off_rS = off_lamp + 8 * MS_LLD;                      // [8][RLD] ratio v./Lambda
@@ -70,8 +83,8 @@ struct MsLayout {
   static constexpr size_t off_rN = off_WnP + (size_t)((S * MS_RA + 1) & ~1);   // [2][8] ratio of the tail row (by parity)
   static constexpr size_t off_hsum = off_rN + 16;                              // [2][8]
   static constexpr size_t off_bar = off_hsum + 16;                             // 2 mbarriers
-  static constexpr size_t off_slot = off_bar + 2;                              // 8 ints
-  static constexpr size_t doubles = off_slot + 4;
+  static constexpr size_t off_slot = off_bar + 2;                              // 8 ints, then the TMEM base address
+  static constexpr size_t doubles = off_slot + 6;
   static constexpr size_t bytes = doubles * sizeof(double);
 };
 
@@ -116,7 +129,10 @@ static_assert(MS_RA == 50, "ms_pk covers the 25 atom pairs of R_a = 50");
 //   hb  : shared-memory address of hS[li][2 lj]              (B fragments: atoms 8u + 2 lj + {0,1} of stream li)
 //   wX  : address of the stream's private columns + 16 lane  (row pair `lane` of atom k at (wX ^ ((k & 7) << 4)) + 512 k)
 //   hp  : address of hS[warp][PRIV0]
-template <int MODE, bool PRIV>
+//   PRIV : 0 = no private work, 1 = private columns in shared memory (wX), 2 = in tensor memory (wX = TMEM address of the
+//          lane quadrant; pattern A)
+__device__ __forceinline__ double ms_u2d(unsigned lo, unsigned hi) { return __hiloint2double((int)hi, (int)lo); }
+template <int MODE, int PRIV>
 __device__ __forceinline__ void ms_pass_a(const double (&Wa)[2 * MS_KT], unsigned hb, int lj, unsigned wX, unsigned hp,
                                           double& c0, double& c1, double& l0, double& l1) {
   double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
@@ -135,7 +151,7 @@ __device__ __forceinline__ void ms_pass_a(const double (&Wa)[2 * MS_KT], unsigne
       dmma884(p0, p1, Wa[2 * u], hh.x);
       dmma884(q0, q1, Wa[2 * u + 1], hh.y);
     }
-    if (PRIV) {
+    if (PRIV == 1) {
 #pragma unroll
       for (int t = (u * PSTEPS) / MS_KT; t < ((u + 1) * PSTEPS) / MS_KT; ++t) {
         const int k = ms_pk(t);
@@ -146,6 +162,22 @@ __device__ __forceinline__ void ms_pass_a(const double (&Wa)[2 * MS_KT], unsigne
         a1 = fma(w0.y, hh.x, a1);
         b0 = fma(w1.x, hh.y, b0);
         b1 = fma(w1.y, hh.y, b1);
+      }
+    }
+    if (PRIV == 2) {
+      // tensor memory is lane-private: no swizzle, atoms in natural order; the loads of this step's atom pairs were issued
+      // before the mma above would have been ideal, but one wait covers them all and the mma hide most of the latency
+#pragma unroll
+      for (int t = (u * PSTEPS) / MS_KT; t < ((u + 1) * PSTEPS) / MS_KT; ++t) {
+        const int k = 2 * t;
+        unsigned w[8];
+        umma::tmem_ld8(wX + (unsigned)(MS_TM_A + 4 * k), w);
+        const double2 hh = ms_lds2(hp + 8u * (unsigned)k);
+        umma::tmem_wait_ld();
+        a0 = fma(ms_u2d(w[0], w[1]), hh.x, a0);
+        a1 = fma(ms_u2d(w[2], w[3]), hh.x, a1);
+        b0 = fma(ms_u2d(w[4], w[5]), hh.y, b0);
+        b1 = fma(ms_u2d(w[6], w[7]), hh.y, b1);
       }
     }
   }
@@ -162,7 +194,7 @@ __device__ __forceinline__ void ms_pass_a(const double (&Wa)[2 * MS_KT], unsigne
 //   wx0 / wx1 : (column base of the lane's atom) ^ ((atom & 7) << 4)
 //   ct0 / ct1 : the lane's two KL terms v log(v / Lambda) - v + Lambda of the ratio step (sparse_nmf.m:250); they are evaluated
 //   here, off the critical path, and summed over the 8 rows of the warp's tile into costw_w[stream]
-template <int NT, bool PRIV>
+template <int NT, int PRIV>
 __device__ __forceinline__ void ms_pass_b(const double (&Wb)[3][16], unsigned rb, unsigned rp, unsigned wx0, unsigned wx1,
                                           double (&g)[3][2], double& ga, double& gb, const double (&v)[2], const double (&lam)[2],
                                           const double (&rat)[2], const double2* __restrict__ log_tab, double* __restrict__ costw_w,
@@ -186,7 +218,7 @@ __device__ __forceinline__ void ms_pass_b(const double (&Wb)[3][16], unsigned rb
     for (int q = 0; q < NT; ++q) dmma884(g[q][0], g[q][1], Wb[q][2 * u], rr.x);
 #pragma unroll
     for (int q = 0; q < NT; ++q) dmma884(g[q][0], g[q][1], Wb[q][2 * u + 1], rr.y);
-    if (PRIV) {
+    if (PRIV == 1) {
       const unsigned b0 = wx0 ^ ((unsigned)u << 4), b1 = wx1 ^ ((unsigned)u << 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -199,16 +231,32 @@ __device__ __forceinline__ void ms_pass_b(const double (&Wb)[3][16], unsigned rb
         y1 = fma(w1.y, r2.y, y1);
       }
     }
+    if (PRIV == 2) {   // wx0 = TMEM address of the lane quadrant; pattern B: 8 columns per row pair (both atoms of the lane)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = 4 * u + j;
+        unsigned w[8];
+        umma::tmem_ld8(wx0 + (unsigned)(MS_TM_B + 8 * p), w);
+        const double2 r2 = ms_lds2(rp + 16u * (unsigned)p);
+        umma::tmem_wait_ld();
+        x0 = fma(ms_u2d(w[0], w[1]), r2.x, x0);
+        x1 = fma(ms_u2d(w[2], w[3]), r2.y, x1);
+        y0 = fma(ms_u2d(w[4], w[5]), r2.x, y0);
+        y1 = fma(ms_u2d(w[6], w[7]), r2.y, y1);
+      }
+    }
   }
   ga = x0 + x1;
   gb = y0 + y1;
 }
 
-template <int S>
+template <int S, int TS>
 __global__ void __cluster_dims__(MS_CL, 1, 1) __launch_bounds__(MS_THREADS, 1)
 hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, const double* __restrict__ h_init, int g_step,
                  const double2* __restrict__ log_tab, const double* __restrict__ colstat, int n_active) {
-  using L = MsLayout<S>;
+  using L = MsLayout<S, TS>;
+  constexpr int SS = S - TS;
+  static_assert(TS == 0 || (TS <= 4 && SS % 4 == 0), "stream n >= SS uses the TMEM quadrant of warp n: (n - SS) == n % 4");
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int grp = (int)(blockIdx.x / MS_CL);
@@ -267,8 +315,19 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
+  // ---- tensor memory for the private columns of the last TS streams (all 512 columns: one CTA per SM) ----
+  unsigned tq = 0;   // TMEM address of this warp's lane quadrant
+  if (TS > 0) {
+    unsigned* tbase_s = reinterpret_cast<unsigned*>(slot_s + 8);
+    if (warp == 0) umma::tmem_alloc(tbase_s, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    tq = *tbase_s + ((unsigned)(32 * (warp & 3)) << 16);
+  }
+
   // ---- private columns: 16-byte cp.async into the swizzled layout (pair p of atom k at slot p ^ (k & 7)) ----
-  for (int c = tid; c < S * MS_RA * 32; c += MS_THREADS) {
+  for (int c = tid; c < SS * MS_RA * 32; c += MS_THREADS) {
     const int n = c / (MS_RA * 32), rem = c - n * (MS_RA * 32);
     const int k = rem >> 5, p = rem & 31;
     const int slot = slot_s[n];
@@ -282,6 +341,39 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  // streams SS .. S-1: warp n writes stream n into its TMEM quadrant, in both access patterns
+  if (TS > 0 && warp >= SS && warp < S) {
+    const int slot = slot_s[warp];
+    const double* Bp = slot >= 0 ? st.Bd[st.bd_sel[slot]] + (size_t)slot * d.R_d * LDF + f0 : nullptr;
+    // pattern A: lane <-> row pair, columns 4k .. 4k+3 = W[2 lane .. +1][k]
+#pragma unroll 5
+    for (int k = 0; k < MS_RA; k += 2) {
+      double2 w0 = make_double2(0.0, 0.0), w1 = w0;
+      if (Bp) {
+        w0 = *reinterpret_cast<const double2*>(Bp + (size_t)k * LDF + 2 * lane);
+        w1 = *reinterpret_cast<const double2*>(Bp + (size_t)(k + 1) * LDF + 2 * lane);
+      }
+      const unsigned r[8] = {(unsigned)__double2loint(w0.x), (unsigned)__double2hiint(w0.x), (unsigned)__double2loint(w0.y),
+                             (unsigned)__double2hiint(w0.y), (unsigned)__double2loint(w1.x), (unsigned)__double2hiint(w1.x),
+                             (unsigned)__double2loint(w1.y), (unsigned)__double2hiint(w1.y)};
+      umma::tmem_st8(tq + (unsigned)(MS_TM_A + 4 * k), r);
+    }
+    // pattern B: lane <-> atoms lane and 32 + lane, columns 8p .. 8p+7 = rows 2p, 2p+1 of both
+    const int b0 = lane, b1 = 32 + lane < MS_RA ? 32 + lane : lane;
+#pragma unroll 4
+    for (int p = 0; p < MS_ROWS / 2; ++p) {
+      double2 w0 = make_double2(0.0, 0.0), w1 = w0;
+      if (Bp) {
+        w0 = *reinterpret_cast<const double2*>(Bp + (size_t)b0 * LDF + 2 * p);
+        w1 = *reinterpret_cast<const double2*>(Bp + (size_t)b1 * LDF + 2 * p);
+      }
+      const unsigned r[8] = {(unsigned)__double2loint(w0.x), (unsigned)__double2hiint(w0.x), (unsigned)__double2loint(w0.y),
+                             (unsigned)__double2hiint(w0.y), (unsigned)__double2loint(w1.x), (unsigned)__double2hiint(w1.x),
+                             (unsigned)__double2loint(w1.y), (unsigned)__double2hiint(w1.y)};
+      umma::tmem_st8(tq + (unsigned)(MS_TM_B + 8 * p), r);
+    }
+    umma::tmem_wait_st();
+  }
 
   // ---- shared columns -> registers, in both fragment layouts ----
   auto shared_col = [&](int a) -> const double* {
@@ -356,7 +448,8 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   // ---- norms / sums of the private columns over this CTA's rows (sparse_nmf.m:157-160,192): partials to the owners ----
   const int a0 = lane, a1 = 32 + lane;
   const bool has1 = a1 < MS_RA;
-  const double* wp_mine = Wp + (size_t)(warp < S ? warp : 0) * MS_RA * MS_ROWS;
+  const bool in_tmem = TS > 0 && warp >= SS && warp < S;     // this warp's stream has its private columns in tensor memory
+  const double* wp_mine = Wp + (size_t)(warp < SS ? warp : 0) * MS_RA * MS_ROWS;
   // pair p of atom a sits at byte (base(a) ^ ((a & 7) << 4)) ^ (p << 4): the column base is 512-byte aligned.  Lanes without a
   // second atom read the first one again (no predicated loads); their result is never pushed.
   const int a1c = has1 ? a1 : a0;
@@ -368,7 +461,19 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   }
   if (warp < S) {
     double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;
-    if (own_stream) {
+    if (own_stream && in_tmem) {
+#pragma unroll 4
+      for (int p = 0; p < 32; ++p) {
+        unsigned w[8];
+        umma::tmem_ld8(tq + (unsigned)(MS_TM_B + 8 * p), w);
+        umma::tmem_wait_ld();
+        const double x0 = ms_u2d(w[0], w[1]), x1 = ms_u2d(w[2], w[3]), y0 = ms_u2d(w[4], w[5]), y1 = ms_u2d(w[6], w[7]);
+        s1a += x0 + x1;
+        s2a = fma(x0, x0, fma(x1, x1, s2a));
+        s1b += y0 + y1;
+        s2b = fma(y0, y0, fma(y1, y1, s2b));
+      }
+    } else if (own_stream) {
 #pragma unroll 8
       for (int p = 0; p < 32; ++p) {
         const double2 w0 = ms_lds2(wx0 ^ ((unsigned)p << 4)), w1 = ms_lds2(wx1 ^ ((unsigned)p << 4));
@@ -377,6 +482,8 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
         s1b += w1.x + w1.y;
         s2b = fma(w1.x, w1.x, fma(w1.y, w1.y, s2b));
       }
+    }
+    if (own_stream) {
       if (tail_rank) {
         const double t0 = WnP[warp * MS_RA + a0], t1 = WnP[warp * MS_RA + a1c];
         s1a += t0;
@@ -446,7 +553,8 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   const unsigned rb = (unsigned)__cvta_generic_to_shared(rS + (size_t)li * MS_RLD + 2 * lj);   // B fragments of the g pass
   const unsigned hp_mine = (unsigned)__cvta_generic_to_shared(hS + (size_t)(warp < S ? warp : 0) * MS_HLD + MS_PRIV0);
   const unsigned rp_mine = (unsigned)__cvta_generic_to_shared(rS + (size_t)(warp < S ? warp : 0) * MS_RLD);
-  const unsigned wX = (unsigned)__cvta_generic_to_shared(wp_mine) + 16u * (unsigned)lane;
+  const unsigned wX = in_tmem ? tq : (unsigned)__cvta_generic_to_shared(wp_mine) + 16u * (unsigned)lane;
+  const unsigned wB0 = in_tmem ? tq : wx0;   // first operand of the g pass: TMEM quadrant or swizzled column base
   double* lamp_mine = lam_p + (size_t)(warp < S ? warp : 0) * MS_LLD;
   const int frow = 8 * warp + li;
 
@@ -501,11 +609,12 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     double c0, c1;
     if (priv) {
       double l0, l1;
-      ms_pass_a<0, true>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      if (in_tmem) ms_pass_a<0, 2>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      else ms_pass_a<0, 1>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
       *reinterpret_cast<double2*>(lamp_mine + 2 * lane) = make_double2(l0, l1);
     } else {
       double l0, l1;
-      ms_pass_a<0, false>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      ms_pass_a<0, 0>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
     }
     if (tail_rank && warp < S) {
       double ctn = 0.0, rn = 0.0;
@@ -539,11 +648,13 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
       double g[3][2], ga, gb;
       const bool nt3 = warp < MS_KT - 16;
       if (nt3) {
-        if (priv) ms_pass_b<3, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
-        else ms_pass_b<3, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
+        // (the three-tile warps 0..2 never own a TMEM stream: SS >= 4 whenever TS > 0)
+        if (priv) ms_pass_b<3, 1>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
+        else ms_pass_b<3, 0>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
       } else {
-        if (priv) ms_pass_b<2, true>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
-        else ms_pass_b<2, false>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
+        if (priv && in_tmem) ms_pass_b<2, 2>(Wb, rb, rp_mine, wB0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
+        else if (priv) ms_pass_b<2, 1>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
+        else ms_pass_b<2, 0>(Wb, rb, rp_mine, wx0, wx1, g, ga, gb, v, lamv, ratv, log_tab, costw + warp * 8, li, lj);
       }
       // the cost partials of all warps are summed by warp 7: the others only arrive at named barrier 1 (non-blocking)
       if (warp != MS_WARPS - 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
@@ -647,7 +758,7 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   // X_hat = B_x A_x
   {
     double c0, c1, l0, l1;
-    ms_pass_a<1, false>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+    ms_pass_a<1, 0>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int n = 2 * lj + e;
@@ -662,10 +773,11 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
   {
     double c0, c1, l0, l1;
     if (own_stream) {
-      ms_pass_a<2, true>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      if (in_tmem) ms_pass_a<2, 2>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      else ms_pass_a<2, 1>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
       *reinterpret_cast<double2*>(lamp_mine + 2 * lane) = make_double2(l0, l1);
     } else {
-      ms_pass_a<2, false>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
+      ms_pass_a<2, 0>(Wa, hb, lj, wX, hp_mine, c0, c1, l0, l1);
     }
     if (tail_rank && own_stream) {
       const double x = tail_lambda(2);
@@ -680,6 +792,7 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
     }
   }
   cluster.sync();  // nobody may exit while a peer can still push into its shared memory
+  if (TS > 0 && warp == 0) umma::tmem_dealloc(tq, 512);   // warp 0's quadrant starts at lane 0: tq is the address tcgen05.alloc returned
   MS_TICK(11);
 #ifdef SNMFNAT_MS_PROBE
   if (probe) atomicAdd(&g_ms_probe[15], 1ull);
@@ -687,17 +800,27 @@ hsolve_ms_kernel(OnlineDims d, OnlineScalars sc, SlotState st, FrameArrays fr, c
 }
 
 // ---- host side ----
-constexpr int MS_S = 7;   // streams per cluster: 7 x 25.6 KB of private columns + 43 KB of exchange buffers per CTA
+// Streams per cluster.  <8, 4>: four streams' private columns in shared memory (102 KB), four in tensor memory, the mma N
+// dimension full.  <7, 0> (SNMFNAT_HSOLVE=ms7): all seven in shared memory (179 KB + 43 KB of exchange buffers).
+constexpr int MS_S = 8, MS_TS = 4;
+static bool ms_use_tmem() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SNMFNAT_HSOLVE");
+    v = (e && std::string(e) == "ms7") ? 0 : 1;
+  }
+  return v == 1;
+}
 
 bool hsolve_ms_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
   const int E = d.F - MS_CL * MS_ROWS;
   if (E < 0 || E > 1) return false;
   if (d.R_x != MS_RX || d.R_d != MS_RF + MS_RA || d.R_a != MS_RA || d.R != MS_RX + MS_RF + MS_RA) return false;
   if (d.LDF < d.F || (d.LDF & 1)) return false;
-  return (int)MsLayout<MS_S>::bytes <= ctx->max_smem_optin;
+  return (int)MsLayout<7, 0>::bytes <= ctx->max_smem_optin;
 }
 
-int hsolve_ms_streams() { return MS_S; }
+int hsolve_ms_streams() { return ms_use_tmem() ? MS_S : 7; }
 
 void launch_ms_colstat(snmfnat_ctx* ctx, const OnlineDims& d, const double* Bx, const double* Bd_fix, double* colstat) {
   ms_colstat_kernel<<<(MS_KS + 7) / 8, 256, 0, ctx->stream>>>(Bx, Bd_fix, d.F, d.LDF, colstat);
@@ -705,12 +828,13 @@ void launch_ms_colstat(snmfnat_ctx* ctx, const OnlineDims& d, const double* Bx, 
   check_launch(ctx, "ms_colstat_kernel");
 }
 
-void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
-                      const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
-  SN_REQUIRE(st.ms_colstat != nullptr, SNMFNAT_EINVAL, "multi-stream H-solve: column statistics of the shared basis are missing");
-  const size_t bytes = MsLayout<MS_S>::bytes;
-  SN_CUDA(cudaFuncSetAttribute(hsolve_ms_kernel<MS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  const int groups = (n_active + MS_S - 1) / MS_S;
+template <int S, int TS>
+static void launch_ms_variant(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                              const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
+  const size_t bytes = MsLayout<S, TS>::bytes;
+  auto kern = hsolve_ms_kernel<S, TS>;
+  SN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  const int groups = (n_active + S - 1) / S;
   static bool reported = false;
   if (!reported && getenv("SNMFNAT_DEBUG")) {
     reported = true;
@@ -723,12 +847,19 @@ void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars
     at[0].val.clusterDim.x = MS_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int nc = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, hsolve_ms_kernel<MS_S>, &cfg);
-    fprintf(stderr, "snmfnat: hsolve_ms_kernel<%d>: %zu bytes of shared memory, max active clusters = %d (%s)\n", MS_S, bytes, nc,
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    fprintf(stderr, "snmfnat: hsolve_ms_kernel<%d,%d>: %zu bytes of shared memory, max active clusters = %d (%s)\n", S, TS, bytes, nc,
             cudaGetErrorString(e));
   }
-  hsolve_ms_kernel<MS_S><<<dim3(MS_CL * groups), dim3(MS_THREADS), bytes, ctx->stream>>>(
-      d, sc, st, fr, h_init, g_step, log_table(ctx), st.ms_colstat, n_active);
+  kern<<<dim3(MS_CL * groups), dim3(MS_THREADS), bytes, ctx->stream>>>(d, sc, st, fr, h_init, g_step, log_table(ctx), st.ms_colstat,
+                                                                        n_active);
+}
+
+void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                      const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
+  SN_REQUIRE(st.ms_colstat != nullptr, SNMFNAT_EINVAL, "multi-stream H-solve: column statistics of the shared basis are missing");
+  if (ms_use_tmem()) launch_ms_variant<MS_S, MS_TS>(ctx, d, sc, st, fr, h_init, n_active, g_step);
+  else launch_ms_variant<7, 0>(ctx, d, sc, st, fr, h_init, n_active, g_step);
   count_launch(ctx);
   check_launch(ctx, "hsolve_ms_kernel");
 #ifdef SNMFNAT_MS_PROBE

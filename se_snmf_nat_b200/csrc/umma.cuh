@@ -145,6 +145,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&r)[16]
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// 8 consecutive 32-bit columns of the calling lane's TMEM lane (32x32b: lane i of the warp <-> TMEM lane 32*(warp%4)+i)
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[32]) { tmem_ld32(addr, r); }
 __device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[16]) { tmem_ld16(addr, r); }
 __device__ __forceinline__ void tmem_st(uint32_t addr, const uint32_t (&r)[32]) { tmem_st32(addr, r); }

@@ -336,35 +336,43 @@ def test_smoke_entry():
 
 
 _VARIANT_SCRIPT = r"""
-import sys
+import os, sys
 import numpy as np
 sys.path.insert(0, {root!r})
 from se_snmf_nat_b200 import api
 from oracle import snmf_oracle as O
 g = {golden!r}
 bases = np.load(g + "/bases.npz"); wavs = np.load(g + "/wavs.npz"); rng = np.load(g + "/rng_seed1.npz")
-pcm = wavs["M03_in"][4000:4000 + 160 * 150]
-out, st = api.enhance_batch([pcm], api.default_p(), bases["B_DFT_x"], bases["B_DFT_d"], h_init=rng["h_init"],
-                            Ad_blk_init=rng["Ad_blk"], return_stats=True)
-tr = []
-ref, _ = O.enhance_utterance(pcm, O.default_params(), bases["B_DFT_x"], bases["B_DFT_d"], h_init=rng["h_init"],
-                             Ad_blk_init=rng["Ad_blk"], trace=tr)
-assert len(out[0]) == len(ref)
-d = int(np.abs(out[0].astype(int) - ref.astype(int)).max())
+n = int(os.environ.get("SNMFNAT_TEST_NUTT", "1"))
+hops = 150 if n == 1 else 60
+pcms = [wavs["M03_in"][4000 + 3000 * i:4000 + 3000 * i + 160 * (hops - 3 * i)] for i in range(n)]
+ads = np.stack([rng["Ad_blk"]] * n)
+outs, st = api.enhance_batch(pcms, api.default_p(), bases["B_DFT_x"], bases["B_DFT_d"], h_init=rng["h_init"],
+                             Ad_blk_init=ads, return_stats=True)
+hi = wi = d = 0
+for pcm, out in zip(pcms, outs):
+    tr = []
+    ref, _ = O.enhance_utterance(pcm, O.default_params(), bases["B_DFT_x"], bases["B_DFT_d"], h_init=rng["h_init"],
+                                 Ad_blk_init=rng["Ad_blk"], trace=tr)
+    assert len(out) == len(ref)
+    d = max(d, int(np.abs(out.astype(int) - ref.astype(int)).max()))
+    hi += sum(int(t["h_iters"]) for t in tr); wi += sum(int(t["w_iters"]) for t in tr)
 assert d <= 1, d
-hi = sum(int(t["h_iters"]) for t in tr); wi = sum(int(t["w_iters"]) for t in tr)
 assert st["h_iters"] == hi, (st["h_iters"], hi)
 assert st["w_iters"] == wi, (st["w_iters"], wi)
 print("variant ok", d, st["h_iters"], st["w_iters"])
 """
 
 
-@pytest.mark.parametrize("env", [dict(SNMFNAT_FORCE_GENERIC="1"), dict(SNMFNAT_HSOLVE="ms"), dict(SNMFNAT_HSOLVE="single")],
-                         ids=["generic_kernels", "hsolve_ms_forced", "hsolve_single_forced"])
+@pytest.mark.parametrize("env", [dict(SNMFNAT_FORCE_GENERIC="1"), dict(SNMFNAT_HSOLVE="ms"), dict(SNMFNAT_HSOLVE="single"),
+                                 dict(SNMFNAT_HSOLVE="ms7", SNMFNAT_GROUPS="1", SNMFNAT_TEST_NUTT="9")],
+                         ids=["generic_kernels", "hsolve_ms_forced", "hsolve_single_forced", "hsolve_ms7_shared_memory_only"])
 def test_alternative_kernel_generations_agree_with_oracle(env):
     """SNMFNAT_FORCE_GENERIC=1 selects the any-geometry kernels (the ones every non-shipped rank/frame-length falls back
     to); SNMFNAT_HSOLVE=ms / single force the multi-stream (one live stream in a 7-stream cluster) / the per-stream H-solve
-    whatever the number of active streams.  All must reproduce the oracle.  The switches are read once per process."""
+    whatever the number of active streams; SNMFNAT_HSOLVE=ms7 selects the 7-stream all-shared-memory variant of the
+    multi-stream kernel instead of the 8-stream one with four streams in tensor memory (it needs >= 7 active streams, so that
+    case runs a 9-utterance batch).  All must reproduce the oracle.  The switches are read once per process."""
     import os
     import subprocess
     import sys
