@@ -3,8 +3,8 @@
 // Reference: run_basis_train.m:80-91 calls sparse_nmf (src/sparse_nmf.m:71-292) with W and H both updated, KL
 // divergence, on the power spectrogram of the training corpus.  Here every rank holds T_local frames of V (and the
 // matching columns of H); an iteration is
-//     hphase_kernel   H-update of the local frames (+ cost of the state it started from, sum(H',2), tail row)
-//     wphase_kernel   G = (V ./ (W*H')) * H''   partial over the local frames
+//     hphase2_kernel  H-update of the local frames (+ cost of the state it started from, sum(H',2), tail row)
+//     wphase2_kernel  G = (V ./ (W*H')) * H''   partial over the local frames
 //     reduce          fixed-order sum of the per-CTA partials into  acc = [G (F x Kp) | sum(H',2) (Kp)]
 //     ncclAllReduce   acc over ranks (the only collective: (F*Kp + Kp) floats)
 //     wupdate_kernel  W-update + column normalisation (sparse_nmf.m:214-243), replicated on every rank
@@ -68,17 +68,14 @@ struct snmfnat_train {
   int F = 0, K = 0, Kp = 0, nkb = 0, ldv = 0;
   int64_t T = 0;
   double sparsity = 0.0;
-  int tail_row = -1, nchunk = 0, ngroups = 0, grid_h = 0, ntiles = 0, nstages = 0;
-  int nc = 32, nst_h = 2, nst_w = 2;  // streamed-tile rows and pipeline depths (shared-memory budget)
+  int tail_row = -1, nchunk = 0, ngroups = 0, grid_h = 0, ntiles = 0;
   int64_t ldt = 0;
   DevBuf<float> V, Vt, H[2], W0, Wm[2], Wt[2], invden[2], wtail[2], wn, acc, hs_part, gt_part, Gpart;
   DevBuf<double> cost_part, scal;
-  DevBuf<float> dbg_h, dbg_w;  // diagnostics (SNMFNAT_TRAIN_DEBUG=1)
+  bool probe = false;  // SNMFNAT_TRAIN_DEBUG=1: the kernels print the MMA issuer's wait/issue clocks of the first iteration
   int cur_h = 0, cur_w = 0;
-  CUtensorMap mH128[2], mHk[2], mHm[2], mWk[2], mWm[2], mW128[2];
-  // second-generation kernels (train_kernels2.cuh): 128-row K-major tiles (mH128 / mW128) and 16-row MN-major slices
-  CUtensorMap mHm16[2], mWm16[2];
-  int v2 = 1;                 // SNMFNAT_TRAIN_V1=1 selects the first-generation kernels
+  // TMA views of H and of the operand copy of W (train_kernels2.cuh): 128-row K-major tiles and 16-row MN-major slices
+  CUtensorMap mH128[2], mW128[2], mHm16[2], mWm16[2];
   int nblk_h = 0, nlast_h = 0, nblocks_w = 0, nu = 2;
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -280,14 +277,7 @@ __global__ void transpose_v_kernel(const float* __restrict__ V, int ldv, int F, 
   }
 }
 
-size_t hphase_smem(const snmfnat_train* t) {
-  return t->nc == 16 ? hphase_smem_bytes<16>(t->nkb, t->nst_h) : hphase_smem_bytes<32>(t->nkb, t->nst_h);
-}
-size_t wphase_smem(const snmfnat_train* t) {
-  return t->nc == 16 ? wphase_smem_bytes<16>(t->nkb, t->nst_w) : wphase_smem_bytes<32>(t->nkb, t->nst_w);
-}
-
-void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
+void launch_hphase(snmfnat_train* t, int update, int want_cost) {
   HPhase2Args a;
   a.F = t->F; a.Fm = t->tail_row >= 0 ? t->F - 1 : t->F; a.Kp = t->Kp; a.nkb = t->nkb;
   a.nh = t->nblk_h; a.nlast = t->nlast_h;
@@ -297,7 +287,7 @@ void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
   a.Vt = t->Vt.p;
   a.invden = t->invden[t->cur_w].p; a.wtail = t->wtail[t->cur_w].p;
   a.hs_part = t->hs_part.p; a.gt_part = t->gt_part.p; a.cost_part = t->cost_part.p;
-  a.probe = (update && t->iters_done == 0 && t->dbg_h.p) ? 1 : 0;
+  a.probe = (update && t->iters_done == 0 && t->probe) ? 1 : 0;
   a.nu = t->nu;
   const int ch = t->cur_h, cw = t->cur_w;
   hphase2_kernel<<<t->grid_h, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1],
@@ -306,66 +296,18 @@ void launch_hphase2(snmfnat_train* t, int update, int want_cost) {
   check_launch(t->ctx, "hphase2_kernel");
 }
 
-void launch_wphase2(snmfnat_train* t, int hbuf) {
+void launch_wphase(snmfnat_train* t, int hbuf) {
   WPhase2Args a;
   a.F = t->F; a.Kp = t->Kp; a.nkb = t->nkb;
   a.nchunk = t->nchunk; a.ngroups = t->ngroups; a.nblocks = t->nblocks_w; a.ldv = t->ldv; a.T = t->T;
   a.V = t->V.p; a.Gpart = t->Gpart.p;
   a.nu = t->nu;
-  a.probe = (t->iters_done == 0 && t->dbg_w.p) ? 1 : 0;
+  a.probe = (t->iters_done == 0 && t->probe) ? 1 : 0;
   const int grid = t->nchunk * t->ngroups, cw = t->cur_w;
   wphase2_kernel<<<grid, THREADS, phase2_smem_bytes(t->nkb, t->nu), t->ctx->stream>>>(t->mW128[cw], t->mH128[hbuf],
                                                                                        t->mHm16[hbuf], a);
   count_launch(t->ctx);
   check_launch(t->ctx, "wphase2_kernel");
-}
-
-void launch_hphase(snmfnat_train* t, int update, int want_cost) {
-  if (t->v2) {
-    launch_hphase2(t, update, want_cost);
-    return;
-  }
-  HPhaseArgs a;
-  a.F = t->F; a.Kp = t->Kp; a.nkb = t->nkb;
-  a.nch = (t->F + t->nc - 1) / t->nc;
-  const int rem = t->F - (a.nch - 1) * t->nc;
-  a.nlast = (rem + 15) / 16 * 16;
-  a.ntiles = t->ntiles;
-  a.nst = t->nst_h;
-  a.update = update; a.want_cost = want_cost; a.tail_row = t->tail_row;
-  a.T = t->T; a.ldt = t->ldt;
-  a.Vt = t->Vt.p;
-  a.invden = t->invden[t->cur_w].p; a.wtail = t->wtail[t->cur_w].p;
-  a.hs_part = t->hs_part.p; a.gt_part = t->gt_part.p; a.cost_part = t->cost_part.p;
-  a.dbg = (update && t->iters_done == 0) ? t->dbg_h.p : nullptr;
-  const int ch = t->cur_h, cw = t->cur_w;
-  if (t->nc == 16)
-    hphase_kernel<16><<<t->grid_h, THREADS, hphase_smem(t), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1], t->mWk[cw],
-                                                                              t->mWm[cw], a);
-  else
-    hphase_kernel<32><<<t->grid_h, THREADS, hphase_smem(t), t->ctx->stream>>>(t->mH128[ch], t->mH128[ch ^ 1], t->mWk[cw],
-                                                                              t->mWm[cw], a);
-  count_launch(t->ctx);
-  check_launch(t->ctx, "hphase_kernel");
-}
-
-void launch_wphase(snmfnat_train* t, int hbuf) {
-  if (t->v2) {
-    launch_wphase2(t, hbuf);
-    return;
-  }
-  WPhaseArgs a;
-  a.F = t->F; a.Kp = t->Kp; a.nkb = t->nkb;
-  a.nchunk = t->nchunk; a.ngroups = t->ngroups; a.nstages = t->nstages; a.nst = t->nst_w; a.ldv = t->ldv; a.T = t->T;
-  a.V = t->V.p; a.Gpart = t->Gpart.p;
-  a.dbg = t->iters_done == 0 ? t->dbg_w.p : nullptr;
-  const int grid = t->nchunk * t->ngroups, cw = t->cur_w;
-  if (t->nc == 16)
-    wphase_kernel<16><<<grid, THREADS, wphase_smem(t), t->ctx->stream>>>(t->mW128[cw], t->mHk[hbuf], t->mHm[hbuf], a);
-  else
-    wphase_kernel<32><<<grid, THREADS, wphase_smem(t), t->ctx->stream>>>(t->mW128[cw], t->mHk[hbuf], t->mHm[hbuf], a);
-  count_launch(t->ctx);
-  check_launch(t->ctx, "wphase_kernel");
 }
 
 // div of the state the last hphase started from, summed over ranks, on the host (synchronises the stream)
@@ -451,36 +393,19 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
   const int mma_rows = t->tail_row >= 0 ? F - 1 : F;
   t->nchunk = (mma_rows + BM - 1) / BM;
   t->ntiles = (int)((T_local + BM - 1) / BM);
-  // streamed tiles: 32 rows when both swizzled copies of >= 2 stages fit beside the resident tile, else 16
-  t->nc = (t->Kp > 128) ? 16 : 32;
-  if (const char* e = getenv("SNMFNAT_TRAIN_NC")) t->nc = atoi(e) == 16 ? 16 : 32;
-  for (t->nst_h = MAX_STAGES; t->nst_h > 1 && hphase_smem(t.get()) > (size_t)ctx->max_smem_optin;) t->nst_h--;
-  for (t->nst_w = MAX_STAGES; t->nst_w > 1 && wphase_smem(t.get()) > (size_t)ctx->max_smem_optin;) t->nst_w--;
-  t->nstages = (int)((T_local + t->nc - 1) / t->nc);
   t->ldt = (T_local + 3) / 4 * 4;
   t->grid_h = std::min(t->ntiles, ctx->sm_count);
-  t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nstages));
   t->nu = phase2_units(t->nkb, (size_t)ctx->max_smem_optin);
-  t->v2 = (getenv("SNMFNAT_TRAIN_V1") == nullptr && phase2_smem_bytes(t->nkb, t->nu) <= (size_t)ctx->max_smem_optin) ? 1 : 0;
-  if (t->v2) {
-    const int Fm = t->tail_row >= 0 ? F - 1 : F;
-    t->nblk_h = (Fm + HB - 1) / HB;
-    t->nlast_h = (Fm - (t->nblk_h - 1) * HB + 15) / 16 * 16;
-    t->nblocks_w = (int)((T_local + HB - 1) / HB);
-    t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nblocks_w));
-    SN_CUDA(cudaFuncSetAttribute(hphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
-    SN_CUDA(cudaFuncSetAttribute(wphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase2_smem_bytes(t->nkb, t->nu)));
-  }
-  SN_REQUIRE(hphase_smem(t.get()) <= (size_t)ctx->max_smem_optin && wphase_smem(t.get()) <= (size_t)ctx->max_smem_optin,
-             SNMFNAT_EUNSUPPORTED, "shared memory: need %zu / %zu bytes, device offers %d", hphase_smem(t.get()),
-             wphase_smem(t.get()), ctx->max_smem_optin);
-  if (t->nc == 16) {
-    SN_CUDA(cudaFuncSetAttribute(hphase_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hphase_smem(t.get())));
-    SN_CUDA(cudaFuncSetAttribute(wphase_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wphase_smem(t.get())));
-  } else {
-    SN_CUDA(cudaFuncSetAttribute(hphase_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hphase_smem(t.get())));
-    SN_CUDA(cudaFuncSetAttribute(wphase_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wphase_smem(t.get())));
-  }
+  const size_t smem = phase2_smem_bytes(t->nkb, t->nu);
+  SN_REQUIRE(smem <= (size_t)ctx->max_smem_optin, SNMFNAT_EUNSUPPORTED, "shared memory: need %zu bytes, device offers %d",
+             smem, ctx->max_smem_optin);
+  const int Fm = t->tail_row >= 0 ? F - 1 : F;
+  t->nblk_h = (Fm + HB - 1) / HB;
+  t->nlast_h = (Fm - (t->nblk_h - 1) * HB + 15) / 16 * 16;
+  t->nblocks_w = (int)((T_local + HB - 1) / HB);
+  t->ngroups = std::max(1, std::min(ctx->sm_count / t->nchunk, t->nblocks_w));
+  SN_CUDA(cudaFuncSetAttribute(hphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SN_CUDA(cudaFuncSetAttribute(wphase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = ctx->stream;
   t->V.alloc((size_t)T_local * t->ldv);
   t->Vt.alloc((size_t)F * t->ldt);
@@ -507,21 +432,12 @@ int snmfnat_train_create(snmfnat_ctx* ctx, int F, int K, int64_t T_local, double
   t->cost_part.alloc(t->grid_h);
   t->cost_part.zero(st);
   t->scal.alloc(2);
-  if (getenv("SNMFNAT_TRAIN_DEBUG")) {
-    t->dbg_h.alloc(8192 + 2 * 32768);
-    t->dbg_h.zero(st);
-    t->dbg_w.alloc(8192);
-    t->dbg_w.zero(st);
-  }
+  t->probe = getenv("SNMFNAT_TRAIN_DEBUG") != nullptr;
   SN_CUDA(cudaMallocHost(&t->h_scal, 2 * sizeof(double)));
   SN_CUDA(cudaMallocHost(&t->h_hs, t->Kp * sizeof(float)));
   for (int i = 0; i < 2; ++i) {
     const uint64_t pitch = (uint64_t)t->Kp * 4;
     make_map(&t->mH128[i], t->H[i].p, t->Kp, T_local, pitch, BM);
-    make_map(&t->mHk[i], t->H[i].p, t->Kp, T_local, pitch, t->nc);
-    make_map(&t->mHm[i], t->H[i].p, t->Kp, T_local, pitch, t->nc, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    make_map(&t->mWk[i], t->Wt[i].p, t->Kp, F, pitch, t->nc);
-    make_map(&t->mWm[i], t->Wt[i].p, t->Kp, F, pitch, t->nc, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     make_map(&t->mW128[i], t->Wt[i].p, t->Kp, F, pitch, BM);
     make_map_slices(&t->mHm16[i], t->H[i].p, t->nkb, T_local, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     make_map_slices(&t->mWm16[i], t->Wt[i].p, t->nkb, F, pitch, SL, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -715,16 +631,6 @@ int snmfnat_train_get_acc(snmfnat_train* t, float* g, float* hs) {
       for (int f = 0; f < t->F; ++f) g[(size_t)k * t->F + f] = tmp[(size_t)f * t->Kp + k];
   if (hs)
     for (int k = 0; k < t->K; ++k) hs[k] = tmp[(size_t)t->F * t->Kp + k];
-  SN_API_END
-}
-
-// Diagnostics only (not declared in the public header): the first-tile dumps taken when SNMFNAT_TRAIN_DEBUG is set.
-int snmfnat_train_debug_dump(snmfnat_train* t, float* dbg_h, float* dbg_w) {
-  SN_API_BEGIN
-  SN_REQUIRE(t && t->dbg_h.p, SNMFNAT_EINVAL, "debug dumps are off (set SNMFNAT_TRAIN_DEBUG=1 before snmfnat_train_create)");
-  SN_CUDA(cudaStreamSynchronize(t->ctx->stream));
-  SN_CUDA(cudaMemcpy(dbg_h, t->dbg_h.p, t->dbg_h.n * 4, cudaMemcpyDeviceToHost));
-  SN_CUDA(cudaMemcpy(dbg_w, t->dbg_w.p, t->dbg_w.n * 4, cudaMemcpyDeviceToHost));
   SN_API_END
 }
 

@@ -1,4 +1,5 @@
-// Second generation of the dictionary-training kernels (same math and same roles as train_kernels.cuh).
+// The two warp-specialised tcgen05 kernels of a dictionary-training iteration (second generation; shared constants and
+// helpers in train_kernels.cuh).
 //
 // What changed, and why (measured on B200, profiles/r01_train_*): with both operands in shared memory a tcgen05.mma
 // of M = 128 reads its A operand at one 128-byte row per clock, i.e. ~128 clk per instruction whatever N is, while the

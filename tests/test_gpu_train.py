@@ -70,26 +70,6 @@ def test_iterations_match_oracle(api, O, F, K, T, iters):
     np.testing.assert_allclose(out["div"], obj["div"], rtol=2 * TOL)
 
 
-@pytest.mark.parametrize("env", [dict(SNMFNAT_TRAIN_V1="1")], ids=["first_generation"])
-def test_other_kernel_variants_match_oracle(api, O, env, monkeypatch):
-    """The switch is read by snmfnat_train_create: the first-generation 16-row kernels stay selectable and must give
-    the same results."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    F, K, T, iters = 513, 256, 4096, 3
-    V, idx, H0 = make_problem(F, K, T, seed=11)
-    w_ref, h_ref, obj = oracle_run(O, V, idx, H0, iters)
-    tr = api.Train(api.get_context(0), F, K, T, 5.0)
-    try:
-        tr.set_data(V, V[:, idx], H0)
-        out = tr.iterate(iters, want_cost=True)
-        w, h = tr.get_w(), tr.get_h()
-    finally:
-        tr.close()
-    assert rel_err(w_ref, w) < TOL and rel_err(h_ref, h) < TOL
-    np.testing.assert_allclose(out["cost"], obj["cost"], rtol=TOL)
-
-
 def test_cost_is_non_increasing_and_split_calls_agree(api, O):
     """KL multiplicative updates never increase the cost; n iterations in one call == the same n in two calls."""
     F, K, T = 513, 64, 1500

@@ -1,6 +1,5 @@
 """Stage-by-stage check of the tensor-core training kernels against float64 NumPy (diagnosis aid).
     python tools/train_probe.py [F] [K] [T]"""
-import ctypes as C
 import os
 import sys
 from pathlib import Path
@@ -36,29 +35,6 @@ def case(name, V, W0, H0, sparsity=5.0):
     h1 = h * (w.T @ (v / lam)) / np.maximum(w.sum(0)[:, None] + sparsity, FLR)
     out = tr.iterate(1, want_cost=True)
     hg = tr.get_h().astype(np.float64)
-    Kp = tr.Kp
-    dh = np.zeros(8192 + 2 * 32768, np.float32)
-    dw = np.zeros(8192, np.float32)
-    fp = C.POINTER(C.c_float)
-    tr._lib.snmfnat_train_debug_dump.argtypes = [C.c_void_p, fp, fp]
-    api.check(tr._lib.snmfnat_train_debug_dump(tr._h, dh.ctypes.data_as(fp), dw.ctypes.data_as(fp)))
-    nr = min(128, T)
-    nc = 16 if Kp > 128 else 32
-    lam_g = dh[:4096].reshape(128, 32)[:nr, :nc]
-    v_g = dh[4096:8192].reshape(128, 32)[:nr, :nc]
-    hold_g = dh[8192:8192 + 128 * Kp].reshape(128, Kp)[:nr, :K]
-    num_g = dh[8192 + 32768:8192 + 32768 + 128 * Kp].reshape(128, Kp)[:nr, :K]
-    lam_r = (w[:nc] @ h[:, :nr]).T
-    num_r = (w.T @ (v / lam))[:, :nr].T
-    print(f"[{name}]   dump: Lambda(chunk0) rel {rel(lam_g, lam_r):.2e}  V(chunk0) rel {rel(v_g, v[:nc, :nr].T):.2e}  "
-          f"h_old rel {rel(hold_g, h[:, :nr].T):.2e}  Num rel {rel(num_g, num_r):.2e}")
-    print(f"[{name}]   Lambda gpu[0,:4] {lam_g[0,:4]} ref {lam_r[0,:4]};  Num gpu[0,:4] {num_g[0,:4]} ref {num_r[0,:4]}")
-    print(f"[{name}]   Lambda gpu[1,:4] {lam_g[1,:4]} ref {lam_r[1,:4]};  Num gpu[1,:4] {num_g[1,:4]} ref {num_r[1,:4]}")
-    nf = min(nc, T)
-    lamw_g = dw[:4096].reshape(128, 32)[:, :nf]
-    vw_g = dw[4096:8192].reshape(128, 32)[:, :nf]
-    lamw_r = (w[:128] @ hg[:, :nf])
-    print(f"[{name}]   dump W-phase: Lambda'(stage0) rel {rel(lamw_g, lamw_r):.2e}  V rel {rel(vw_g, v[:128, :nf]):.2e}")
     print(f"[{name}] H-update: H' rel {rel(hg, h1):.2e}   max|H'| gpu {hg.max():.3e} ref {h1.max():.3e}")
     if rel(hg, h1) > 1e-2:
         bad = np.abs(hg - h1) > 1e-2 * np.abs(h1).max()
