@@ -16,6 +16,9 @@ struct OnlineDims {
   // the slots a launch covers: slot0 + i * slot_stride, i = 0 .. n_active-1 (interleaved groups run on separate CUDA
   // streams so that the tail of one group's kernel overlaps the next kernel of another group)
   int slot0 = 0, slot_stride = 1;
+  // atoms [upd0, upd1) that the separation solve itself updates (p.basis_update_N / _E, bnmf_sep_event_RT_IS16.m:125-139);
+  // empty for the supervised solve of the shipped settings
+  int upd0 = 0, upd1 = 0;
 };
 
 // Scalars of p used inside the kernels.
@@ -80,6 +83,8 @@ struct SlotState {
   int* ws_perm = nullptr;        // [16][ms_perm_stride]
   int* ws_perm_step = nullptr;   // [16] the step it is valid for
   int* w_last = nullptr;         // [S] passes of the slot's last W-solve
+  // semi-supervised separation solve (online_semi.cu): normalised private copy of the atoms the solve updates
+  double* semi_w = nullptr;      // [S][upd1-upd0][LDF]
 };
 
 // Per-frame arrays shared by the STFT, the solvers and the ISTFT.
@@ -117,6 +122,9 @@ int hsolve_ms_streams();
 void launch_ms_colstat(snmfnat_ctx* ctx, const OnlineDims& d, const double* Bx, const double* Bd_fix, double* colstat);
 void launch_hsolve_ms(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                       const FrameArrays& fr, const double* h_init, int n_active, int g_step);
+// semi-supervised separation solve (online_semi.cu): d.upd0 < d.upd1, one CTA per stream
+void launch_hsolve_semi(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
+                        const FrameArrays& fr, const double* h_init, int n_active, int g_step);
 // SNMFNAT_HSOLVE=ms forces the multi-stream kernel for any number of active streams, =single disables it; by default it
 // runs when at least hsolve_ms_streams() streams are active
 int hsolve_ms_mode();

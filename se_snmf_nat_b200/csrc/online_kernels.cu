@@ -411,6 +411,10 @@ int hsolve_ms_mode() {
 void launch_hsolve(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                    const FrameArrays& fr, const double* h_init, int n_active, int g_step) {
   if (n_active <= 0) return;
+  if (d.upd1 > d.upd0) {   // p.basis_update_N / _E: the solve also updates part of the dictionary
+    launch_hsolve_semi(ctx, d, sc, st, fr, h_init, n_active, g_step);
+    return;
+  }
   if (!force_generic() && st.ms_colstat && hsolve_ms_supported(ctx, d)) {
     const int mode = hsolve_ms_mode();
     if (mode == 1 || (mode == 0 && n_active >= hsolve_ms_streams())) {

@@ -17,8 +17,8 @@ void make_config(snmfnat_ctx* ctx, const snmfnat_params& p, int n2, Config& cfg)
   SN_REQUIRE(p.B_sep_mode == SNMFNAT_SEP_DFT || p.MelConv == 1, SNMFNAT_EUNSUPPORTED,
              "B_sep_mode='Mel' is implemented for MelConv=1 (Mel -> DFT conversion of the separated spectra, :165-172)");
   SN_REQUIRE(p.cf == SNMFNAT_CF_KL, SNMFNAT_EUNSUPPORTED, "online path implements cf='kl' only");
-  SN_REQUIRE(p.basis_update_N == 0 && p.basis_update_E == 0, SNMFNAT_EUNSUPPORTED,
-             "basis_update_N/E (W-update inside the separation solve) is not implemented");
+  SN_REQUIRE((p.basis_update_N == 0 && p.basis_update_E == 0) || p.B_sep_mode == SNMFNAT_SEP_DFT, SNMFNAT_EUNSUPPORTED,
+             "basis_update_N/E (W-update inside the separation solve) is implemented for B_sep_mode='DFT'");
   SN_REQUIRE(p.R_x > 0 && p.R_d > 0 && p.R_a >= 0 && p.R_a <= p.R_d, SNMFNAT_EINVAL, "bad ranks");
   SN_REQUIRE(p.m_a > 0 && p.P_len_l > 0 && p.max_iter >= 0, SNMFNAT_EINVAL, "bad m_a / P_len_l / max_iter");
   SN_REQUIRE(p.DCbin >= 0 && p.DCbin < n2 && p.DCbin_back >= 0 && p.DCbin_back <= n2, SNMFNAT_EINVAL, "bad DCbin");
@@ -30,6 +30,9 @@ void make_config(snmfnat_ctx* ctx, const snmfnat_params& p, int n2, Config& cfg)
   d.F = n2;
   d.LDF = pad_ld(n2);
   d.R_x = p.R_x; d.R_d = p.R_d; d.R = p.R_x + p.R_d; d.R_a = p.R_a; d.m_a = p.m_a; d.P_len_l = p.P_len_l;
+  // bnmf_sep_event_RT_IS16.m:125-139: an if / elseif chain, so basis_update_N wins when both are set
+  if (p.basis_update_N) { d.upd0 = p.R_x; d.upd1 = p.R_x + p.R_d; }
+  else if (p.basis_update_E) { d.upd0 = 0; d.upd1 = p.R_x; }
   OnlineScalars& s = cfg.sc;
   s.flr = p.nonzerofloor;
   s.sparsity = p.sparsity; s.conv_eps = p.conv_eps; s.max_iter = p.max_iter; s.cost_check = p.cost_check;
@@ -83,6 +86,7 @@ void SlotBuffers::alloc(int S_, const OnlineDims& d_) {
   idx_rem.alloc((size_t)S * (d.R_a > 0 ? d.R_a : 1));
   l_offset.alloc(S); n_hops.alloc(S); frame_base.alloc(S);
   stats.alloc(8);
+  if (d.upd1 > d.upd0) semi_w.alloc((size_t)S * (d.upd1 - d.upd0) * LDF);
 }
 
 void SlotBuffers::set_bases(snmfnat_ctx* ctx, const double* B_x, const double* B_d) {
@@ -265,6 +269,7 @@ SlotState SlotBuffers::view() const {
   v.ms_colstat = ms_colstat.p;
   v.ms_perm = ms_perm.p; v.ms_perm_step = ms_perm_step.p; v.ms_ticket = ms_ticket.p; v.ms_perm_stride = S;
   v.ws_perm = ws_perm.p; v.ws_perm_step = ws_perm_step.p; v.w_last = w_last.p;
+  v.semi_w = semi_w.p;
   return v;
 }
 

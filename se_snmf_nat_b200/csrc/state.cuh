@@ -28,6 +28,7 @@ struct SlotBuffers {
   DevBuf<double> ms_colstat;   // norms / sums of the stream-invariant columns (multi-stream H-solve), when supported
   DevBuf<int> ms_perm, ms_perm_step, ms_ticket;   // launch order of the next hop per slot group (SlotState::ms_perm)
   DevBuf<int> ws_perm, ws_perm_step, w_last;      // launch order of the W-solve (SlotState::ws_perm)
+  DevBuf<double> semi_w;       // private copies of the atoms a semi-supervised separation solve updates (SlotState::semi_w)
 
   // Mel separation mode: Mel-sized bases / history / reconstructions next to the DFT-domain state
   int n1 = 0, LD1 = 0;

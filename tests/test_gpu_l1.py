@@ -238,6 +238,28 @@ def test_per_hop_stream_three_event_classes(api, O, bases, wavs, rng_inputs):
     g.close() if hasattr(g, "close") else None
 
 
+def test_per_hop_stream_semi_supervised(api, O, bases, wavs, rng_inputs):
+    """p.basis_update_N = 1 through the per-hop entry (bnmf_sep_event_RT_IS16.m:125-127): the separation solve updates the
+    noise half of the dictionary while it iterates; g.B_DFT_d itself only changes through the adaptation (:336)."""
+    h_init, Ad = rng_inputs
+    over = dict(basis_update_N=1, max_iter=25)
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    pcm = wavs["M03_in"][9000:9000 + 160 * 30]
+    Bx, Bd = bases["B_DFT_x"], bases["B_DFT_d"]
+    g = api.init_buff(Bx, Bd, Bx, Bd, p, Ad_blk_init=Ad)
+    go = O.init_buff(Bx, Bd, Bx, Bd, po, Ad_blk_init=Ad)
+    y = np.zeros(640)
+    for l in range(1, len(pcm) // 160 + 1):
+        y = np.concatenate([y[160:], pcm[(l - 1) * 160:l * 160].astype(float)])
+        _, _, xt, g = api.bnmf_sep_event_RT_IS16(y, l, g, p, h_init=h_init, nargout=1)
+        _, _, xto, go = O.bnmf_sep_event_RT_IS16(y, l, go, po, h_init=h_init)
+        assert int(g["stats"][0]) == go.dbg["h_iters"], l
+        assert np.max(np.abs(xt - xto)) <= 1e-6 * max(1.0, np.max(np.abs(xto))), l
+    assert rel_err(go.B_DFT_d, g["B_DFT_d"]) < 1e-9
+    g.close() if hasattr(g, "close") else None
+
+
 @pytest.mark.parametrize("mel", [False, True], ids=["run_basis_DNMF", "run_basis_DNMF_Mel"])
 def test_dnmf_basis_retraining_matches_oracle(api, O, wavs, mel):
     """run_basis_DNMF.m / run_basis_DNMF_Mel.m: STFT of clean, noise and mixture, activations of

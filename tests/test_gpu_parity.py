@@ -141,6 +141,51 @@ def test_settings_variants(api, O, bases, wavs, rng_inputs, variant):
     assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1
 
 
+@pytest.mark.parametrize("mode", ["semisupervised_N", "update_E_shipped"])
+def test_semi_supervised_separation_solve(api, O, bases, wavs, mode):
+    """p.basis_update_N / _E (bnmf_sep_event_RT_IS16.m:125-139): the per-hop sparse_nmf also updates half of the dictionary
+    while it iterates and the caller keeps only A.  `semisupervised_N` is settings/bak_IS16_results/
+    initial_setting_semisupervised.m (R_d = 50, no adaptation, no block sparsity, Wiener, max_iter = 25, pre-emphasis 0.92,
+    DCfreq 160 Hz -> DCbin 10); `update_E_shipped` flips the other switch on top of the shipped settings, adaptation on."""
+    if mode == "semisupervised_N":
+        over = dict(R_d=50, R_a=50, adapt_train_N=0, init_N_len=10, m_a=40, overlap_m_a=0.5, blk_sparse=0, P_len_k=50,
+                    P_len_l=3, alpha_p=0.6, preemph=0.92, DCbin=10, DCbin_back=10, max_iter=25, basis_update_N=1,
+                    ENHANCE_METHOD="Wiener", alpha_eta=0.95, alpha_d=0.85, beta=2.0)
+        Bd = bases["B_DFT_d"][:, :50].copy()
+        hops = 60
+    else:
+        over = dict(basis_update_E=1)
+        Bd = bases["B_DFT_d"]
+        hops = 40
+    Bx = bases["B_DFT_x"]
+    R = Bx.shape[1] + Bd.shape[1]
+    p = dict(api.default_p(), **over)
+    po = dict(O.default_params(), **over)
+    h_init = O.park_miller(R, 1)
+    Ad = np.random.RandomState(5).rand(p["R_a"], p["m_a"])
+    pcms = [wavs["M03_in"][8000:8000 + 160 * hops], wavs["M04_in"][3000:3000 + 160 * (hops - 7) + 55]]
+    ctx = api.get_context(0)
+    b = api.Batch(ctx, p, Bx, Bd, [len(x) for x in pcms], h_init, np.stack([Ad, Ad]))
+    b.enable_trace(True)
+    b.upload(pcms)
+    b.run()
+    outs = b.download()
+    for i, pcm in enumerate(pcms):
+        tr = []
+        ref, _ = O.enhance_utterance(pcm, po, Bx, Bd, h_init=h_init, Ad_blk_init=Ad, trace=tr)
+        assert np.array_equal(b.trace(i, "h_iters").astype(int), np.array([t["h_iters"] for t in tr])), i
+        assert np.array_equal(b.trace(i, "w_iters").astype(int), np.array([t["w_iters"] for t in tr])), i
+        A = b.trace(i, "A")
+        assert max(rel_err(tr[k]["A"], A[k]) for k in range(len(tr))) <= SPEC_TOL
+        assert snr_db(ref, outs[i]) >= WAVE_SNR_DB
+        assert np.abs(outs[i].astype(int) - ref.astype(int)).max() <= 1, i
+    b.close()
+    # the solve really differs from the supervised one: same inputs, switch off -> other activations
+    p0 = dict(p, basis_update_N=0, basis_update_E=0)
+    sup = api.enhance_batch([pcms[0]], p0, Bx, Bd, h_init=h_init, Ad_blk_init=Ad)[0]
+    assert not np.array_equal(sup, outs[0])
+
+
 def _grow(B, cols, seed):
     """A dictionary with `cols` columns made of perturbed copies of the shipped one (unit-free, non-negative)."""
     rs = np.random.RandomState(seed)
