@@ -25,6 +25,17 @@ void make_config(snmfnat_ctx* ctx, const snmfnat_params& p, int n2, Config& cfg)
   SN_REQUIRE(p.EVENT_NUM >= 1 && p.EVENT_NUM <= SNMFNAT_MAX_CLASSES && p.NOISE_NUM >= 1 &&
                  p.NOISE_NUM <= SNMFNAT_MAX_CLASSES, SNMFNAT_EINVAL, "bad class counts");
   SN_REQUIRE(p.pow > 0, SNMFNAT_EINVAL, "pow must be positive");
+  // class c owns the atoms RANK(c) .. RANK(c+1)-1 (bnmf_sep_event_RT_IS16.m:159-164,181-186): the reference indexes out of
+  // range when a class starts beyond the dictionary (e.g. initial_setting_SNMF_Techwin_201603_RT.m: EVENT_RANK = [1 21 41]
+  // with R_x = 20), and atoms in front of the first class would silently drop out of the reconstruction
+  SN_REQUIRE(p.EVENT_RANK[0] == 1 && p.NOISE_RANK[0] == 1, SNMFNAT_EUNSUPPORTED,
+             "EVENT_RANK(1) / NOISE_RANK(1) must be 1 (atoms in front of the first class are not supported)");
+  for (int i = 1; i < p.EVENT_NUM; ++i)
+    SN_REQUIRE(p.EVENT_RANK[i] > p.EVENT_RANK[i - 1] && p.EVENT_RANK[i] <= p.R_x, SNMFNAT_EINVAL,
+               "EVENT_RANK(%d) = %d: classes must increase and start within R_x = %d", i + 1, p.EVENT_RANK[i], p.R_x);
+  for (int i = 1; i < p.NOISE_NUM; ++i)
+    SN_REQUIRE(p.NOISE_RANK[i] > p.NOISE_RANK[i - 1] && p.NOISE_RANK[i] <= p.R_d, SNMFNAT_EINVAL,
+               "NOISE_RANK(%d) = %d: classes must increase and start within R_d = %d", i + 1, p.NOISE_RANK[i], p.R_d);
   cfg.p = p;
   OnlineDims& d = cfg.d;
   d.F = n2;
