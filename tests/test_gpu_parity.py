@@ -108,6 +108,33 @@ def test_ragged_batch_equals_single_runs(api, O, bases, wavs, rng_inputs):
         assert np.array_equal(alone, outs[i]), "batch composition changed a result"
 
 
+def test_digital_silence_and_constant_input(api, O, bases, rng_inputs):
+    """All-zero PCM (every bin at p.nonzerofloor: the H-solve never meets its stop rule and runs max_iter), a constant
+    (DC only, zeroed by DCbin), and silence followed by a tone: extreme arguments for the reciprocal / logarithm of the
+    solves and for the gates.  Same iteration counts, gates and PCM as the oracle, in one batch (multi-stream kernel off and
+    on: 3 streams -> per-stream kernel; repeated 3x -> 9 streams in one group -> multi-stream kernel)."""
+    h_init, Ad = rng_inputs
+    p, po = api.default_p(), O.default_params()
+    tone = (3000 * np.sin(np.arange(3200) * 0.3)).astype(np.int16)
+    base = [np.zeros(4000, np.int16), np.full(4000, 7, np.int16), np.concatenate([np.zeros(3200, np.int16), tone])]
+    refs = []
+    for pcm in base:
+        tr = []
+        ref, _ = O.enhance_utterance(pcm, po, bases["B_DFT_x"], bases["B_DFT_d"], h_init=h_init, Ad_blk_init=Ad, trace=tr)
+        refs.append((ref, tr))
+    for rep in (1, 3):
+        pcms = base * rep
+        b, outs = run_gpu_traced(api, p, pcms, bases, h_init, np.stack([Ad] * len(pcms)), groups=1)
+        for i in range(len(pcms)):
+            ref, tr = refs[i % 3]
+            assert np.array_equal(b.trace(i, "h_iters").astype(int), np.array([t["h_iters"] for t in tr])), (rep, i)
+            assert np.array_equal(b.trace(i, "w_iters").astype(int), np.array([t["w_iters"] for t in tr])), (rep, i)
+            assert np.array_equal(b.trace(i, "gated").astype(int), np.array([int(t["gated"]) for t in tr])), (rep, i)
+            assert np.isfinite(b.trace(i, "A")).all()
+            assert np.abs(outs[i].astype(int) - ref.astype(int)).max() <= 1, (rep, i)
+        b.close()
+
+
 @pytest.mark.parametrize("variant", ["wiener", "no_adapt", "no_blk", "maxiter25_gap5", "preemph", "R_a20_ma40",
                                      "overlap0.1_ma40", "overlap0.5_ma40", "event3"])
 def test_settings_variants(api, O, bases, wavs, rng_inputs, variant):
