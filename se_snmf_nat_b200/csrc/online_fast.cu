@@ -9,10 +9,10 @@
 //   Per MU iteration: 3 block barriers + 1 cluster barrier; the R-vector g, the cost partial and the tail
 //   terms travel through distributed shared memory.
 //
-// wsolve_fast_kernel : 4-CTA cluster per stream, 17 warps per CTA, one 8-row FP64 tensor-core tile per warp (the 17th
-//   warp of the last CTA takes the F % 8 leftover rows with plain FMAs: a whole tensor-core tile for one row would give
-//   one scheduler of that SM a fifth tile, and every exchange of the cluster would wait for it)
-//   (mma.sync m8n8k4.f64).  W and G = (V./Lambda) H' fragments stay in registers for the whole solve in the SAME
+// wsolve_fast_kernel : 4-CTA cluster per stream, 16 warps per CTA, one 8-row FP64 tensor-core tile per warp
+//   (mma.sync m8n8k4.f64); the F % 8 leftover rows are plain FMAs shared out over the warps of the last CTA at the top of
+//   every pass (a whole tensor-core tile for one row would give one scheduler of that SM a fifth tile; a 17th warp for
+//   them caps every thread at 96 registers).  W and G = (V./Lambda) H' fragments stay in registers for the whole solve in the SAME
 //   fragment layout (the k order of the first GEMM is permuted to match the accumulator layout of the second), the
 //   CTA's slice of V = lambda_d_blk is staged once in shared memory, H is staged once.  Padding rows/columns are
 //   neutral by construction (V pad = floor, W pad = 0, H pad = 0) so the inner loops carry no predicates.
@@ -477,30 +477,26 @@ void launch_hsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScala
 // =====================================================================================================
 // W-solve, fast path
 // =====================================================================================================
-// Two geometries of the same kernel (template parameters CL = CTAs per cluster, TPC = full 8-row tiles per CTA):
-//   <4,16, V in shared memory>  17 warps per CTA, one CTA per SM (the slice of V = lambda_d_blk is staged once)
-//   <8, 8, V from L2>           9 warps per CTA, 82 KB of shared memory -> TWO CTAs (of different streams) per SM: while
-//                               one sits in a reduction / cluster exchange the other keeps the FP64 pipe busy.  V is
-//                               read once per iteration straight from L2 (one group ahead of its use), which is what
-//                               frees the shared memory.
-constexpr int WF_MAX_WARPS = 17;
+// Template parameters: KT = atom tiles of 8, CL = CTAs per cluster, TPC = full 8-row tiles (= warps) per CTA, VSMEM = the
+// CTA's slice of V = lambda_d_blk is staged once in shared memory.  Shipped: <7 or 8, 4, 16, true>, one CTA per SM.  (An
+// <., 8, 8, false> geometry -- V read from L2 once per pass, 82 KB of shared memory, two CTAs of different streams per SM --
+// was measured 10 % slower in round 1: twice the ranks in every exchange.)
 
 template <int KT, int CL, int TPC, bool VSMEM>
 struct WfLayout {
   static constexpr int KMAX = KT * 8;
   static constexpr int XN = 3 * KMAX + 8;
-  static constexpr int WARPS = TPC + 1;      // TPC tile warps + 1 warp for the leftover tile
+  static constexpr int WARPS = TPC;          // one 8-row tensor-core tile per warp; the F % 8 leftover rows are shared out
   int NP, HSd, VS, VROWS;
-  size_t off_H, off_V, off_red, off_recv, off_hs, off_wn, off_tot, off_tab, off_scratch, off_bar, off_Wl, off_Gl, off_rl, bytes;
-  __host__ __device__ WfLayout(int m_a) {
+  int LOWN;                                  // warps that own a 16-column group of the leftover rows
+  size_t off_H, off_V, off_red, off_recv, off_hs, off_wn, off_tot, off_tab, off_scratch, off_bar, off_Wl, off_Gl, off_rl, off_Gp, bytes;
+  __host__ __device__ WfLayout(int m_a, int nleft) {
     NP = (m_a + 15) / 16 * 16;
+    LOWN = NP / 16 < WARPS ? NP / 16 : WARPS;
     HSd = NP + ((2 - NP % 8) + 8) % 8;          // == 2 (mod 8): conflict-free fragment loads in both GEMMs
     VROWS = (TPC + 1) * 8;                      // local rows (leftover tile included)
-    VS = VROWS + 1;                             // odd stride: conflict-free (t, row) fragment reads.  Tried in round 2 and
-                                                // measured slower on the same box (747 -> 771 ms per 1024 x 1.5 s): an even
-                                                // stride with one bulk copy per history column, and an 8-column tail tile
-                                                // (312 instead of 336 mma per pass: the extra code spills at the 96 registers a
-                                                // 17-warp CTA gets)
+    VS = VROWS + 1;                             // odd stride: conflict-free (t, row) fragment reads (an even stride with
+                                                // one bulk copy per history column was measured slower: 2-way conflicts)
     size_t o = 0;
     off_H = o;       o += (size_t)KMAX * HSd;
     off_V = o;       o += VSMEM ? (size_t)NP * VS : 0;
@@ -513,9 +509,11 @@ struct WfLayout {
     off_tab = o;     o += 256;
     off_scratch = o; o += 64;
     off_bar = o;     o += 2;                        // 2 mbarriers
-    off_Wl = o;      o += 8 * KMAX;                 // leftover rows (F % 8 < 8) of W, G and the ratio: plain FMAs on one warp
-    off_Gl = o;      o += 8 * KMAX;
-    off_rl = o;      o += 8 * NP;
+    // leftover rows (F % 8) of W and G, and per owner warp the ratio of its 16 history columns and its partial of G
+    off_Wl = o;      o += (size_t)nleft * KMAX;
+    off_Gl = o;      o += (size_t)nleft * KMAX;
+    off_rl = o;      o += (size_t)LOWN * nleft * 16;
+    off_Gp = o;      o += (size_t)LOWN * nleft * KMAX;
     bytes = o * sizeof(double);
   }
 };
@@ -551,7 +549,7 @@ __device__ unsigned long long g_ws_probe[16];
 #endif
 
 template <int KT, int CL, int TPC, bool VSMEM>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__((TPC + 1) * 32, VSMEM ? 1 : 2)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(WfLayout<KT, CL, TPC, VSMEM>::WARPS * 32, VSMEM ? 1 : 2)
 wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr, int has_trace, int g_step,
                    const double2* __restrict__ log_tab) {
   using LT = WfLayout<KT, CL, TPC, VSMEM>;
@@ -586,7 +584,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   const int g = lane >> 2, tg = lane & 3;
   const int F = d.F, LDF = d.LDF, R_a = d.R_a, R_d = d.R_d, n = d.m_a;
   const double flr = sc.flr;
-  const LT L(n);
+  const LT L(n, F % 8);
   const int HSd = L.HSd, NP = L.NP, VS = L.VS;
 
   extern __shared__ __align__(1024) double smem[];
@@ -616,21 +614,25 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   const double* __restrict__ Vg = st.lam_blk + (size_t)slot * n * LDF;
   const double* __restrict__ Adb = st.Ad_blk + (size_t)slot * n * R_a;
 
-  // tiles: rank r owns full tiles [TPC r, TPC r + TPC); the leftover rows (F % 8) form one more tile on the last rank
+  // tiles: rank r owns full tiles [TPC r, TPC r + TPC), one per warp.  The leftover rows (F % 8; the Nyquist bin for
+  // F = 513) belong to the last rank and are plain FMAs: the warp that owns history-column group tgp (the highest warp
+  // indices: they leave the tile loop first) also works the leftover rows for those 16 columns inside its tile loop, and
+  // the column sums join the CTA partial inside cluster_combine -- no extra barrier, nothing on the critical path.  (A
+  // 17th warp for them costs every thread a quarter of its registers: a 17-warp CTA is allocated like 20 warps, 96
+  // registers per thread instead of 128.)
   const int NFT = F / 8;
   const int nleft = F - NFT * 8;
   const int row0 = rank * TPC * 8;                     // first global row of this CTA's slice
-  int tile_local = warp;                               // local tile index 0..TPC
-  bool tile_valid;
-  if (warp < TPC) tile_valid = (rank * TPC + warp) < NFT;
-  else tile_valid = false;                             // the leftover rows do not use a tensor-core tile (see left_warp)
-  const bool left_warp = (warp == TPC) && (rank == CL - 1) && nleft > 0;
-  int frow = row0 + tile_local * 8 + g;                // global row of this lane's fragment row
-  if (warp == TPC) frow = NFT * 8 + g;
+  const int tile_local = warp;                         // local tile index 0..TPC-1
+  const bool tile_valid = (rank * TPC + warp) < NFT;
+  const bool has_left = (rank == CL - 1) && nleft > 0; // uniform over the CTA
+  const int frow = row0 + tile_local * 8 + g;          // global row of this lane's fragment row
   const bool row_valid = tile_valid && frow < F;
   double* Wl = smem + L.off_Wl;                        // [nleft][KMAX]
-  double* Gl = smem + L.off_Gl;
-  double* rl = smem + L.off_rl;                        // [nleft][NP] ratio of the leftover rows
+  double* Gl = smem + L.off_Gl;                        // [nleft][KMAX]
+  double* rlp = smem + L.off_rl;                       // [LOWN][nleft][16] ratio of the leftover rows, per owner warp
+  double* Glp = smem + L.off_Gp;                       // [LOWN][nleft][KMAX] partial G of the leftover rows, per owner warp
+  const int lown = L.LOWN;
   // local row index inside Vs: tiles 0..TPC-1 -> rows 0..8 TPC-1, leftover tile -> the 8 rows after them
   const int vrow = tile_local * 8 + g;
 
@@ -649,8 +651,8 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       w[j][e] = x;
       gacc[j][e] = 0.0;
     }
-  if (left_warp)
-    for (int i = lane; i < nleft * KMAX; i += 32) {
+  if (has_left)
+    for (int i = tid; i < nleft * KMAX; i += THREADS) {
       const int r = i / KMAX, k = i - r * KMAX;
       Wl[i] = (k < Ru) ? Bcur[(size_t)idx_up[k] * LDF + NFT * 8 + r] : 0.0;
     }
@@ -689,19 +691,29 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         if (g == 0) rw[8 * j + 2 * tg + e] = s;
       }
   };
-  // the same for the leftover rows: lanes <-> atoms, f(r, k)
-  auto left_partial = [&](int which, auto&& f) {
-    double* rw = red + ((size_t)which * WARPS + warp) * KMAX;
-    for (int k = lane; k < KMAX; k += 32) {
-      double s = 0.0;
-      for (int r = 0; r < nleft; ++r) s += f(r, k);
-      rw[k] = s;
+  // what the leftover rows add to the CTA partial of column k (last rank only; evaluated inside cluster_combine by the
+  // thread that sums column k): squares for the norms, or cw_k = sum w / s_k = sum G.*w, with G gathered from the owner
+  // warps' partials and kept in Gl for the update
+  enum { LEFT_SQ = 0, LEFT_SUMS = 1 };
+  auto left_term = [&](int mode, int which, int k) {
+    double s = 0.0;
+    for (int r = 0; r < nleft; ++r) {
+      const double wv = Wl[r * KMAX + k];
+      if (mode == LEFT_SQ) s = fma(wv, wv, s);
+      else if (which == 0) s += wv;
+      else {
+        double gsum = 0.0;
+        for (int o = 0; o < lown; ++o) gsum += Glp[((size_t)o * nleft + r) * KMAX + k];
+        Gl[r * KMAX + k] = gsum;
+        s = fma(gsum, wv, s);
+      }
     }
+    return s;
   };
   // CTA partial (fixed warp order) PUSHED to the CTAs of the cluster (st.async, bytes counted on the receiver's
   // mbarrier: no cluster barrier / fence); totals in rank order -> tot[which][k]
   unsigned rnd = 0;
-  auto cluster_combine = [&](int nwhich, bool with_cost, double* extra_out, bool inv_sqrt = false) {
+  auto cluster_combine = [&](int nwhich, bool with_cost, double* extra_out, int left_mode, bool inv_sqrt = false) {
     __syncthreads();
     const unsigned buf = rnd & 1u, parity = (rnd >> 1) & 1u;
     const unsigned bar = bar0 + 8u * buf;
@@ -714,6 +726,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       double s = 0.0;
 #pragma unroll
       for (int ww = 0; ww < WARPS; ++ww) s += red[((size_t)which * WARPS + ww) * KMAX + k];
+      if (has_left) s += left_term(left_mode, which, k);
       const unsigned la = my_row + 8u * (unsigned)tid;
 #pragma unroll
       for (int c = 0; c < CL; ++c) hf_st_async(hf_mapa(la, c), s, hf_mapa(bar, c));
@@ -733,6 +746,8 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 #pragma unroll
       for (int c = 0; c < CL; ++c) s += rb[(size_t)c * XN + tid];
       tot[tid] = inv_sqrt ? 1.0 / sqrt(s) : s;   // one sqrt + division per column instead of one per element
+      if (inv_sqrt && has_left && tid < Ru)      // the leftover rows are normalised here, by the thread that owns atom k,
+        for (int r = 0; r < nleft; ++r) Wl[r * KMAX + tid] *= tot[tid];   // so that the barrier below publishes them
     }
     if (extra_out) {
       double s = 0.0;
@@ -747,15 +762,13 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   cluster.sync();  // the mbarriers of every CTA are initialised before anybody pushes
   WS_TICK(1);
 
-  // column norms of init_w (sparse_nmf.m:158)
-  __syncwarp();
-  if (left_warp) left_partial(0, [&](int r, int k) { return Wl[r * KMAX + k] * Wl[r * KMAX + k]; });
-  else warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
-  cluster_combine(1, false, nullptr);
+  // column norms of init_w (sparse_nmf.m:158); the cluster barrier above also published Wl inside the CTA
+  warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
+  cluster_combine(1, false, nullptr, LEFT_SQ);
   if (tid < KMAX) wn_s[tid] = (tid < Ru) ? sqrt(tot[tid]) : 1.0;
   __syncthreads();
-  if (left_warp)
-    for (int i = lane; i < nleft * KMAX; i += 32) Wl[i] = Wl[i] / wn_s[i % KMAX];
+  if (has_left && tid < KMAX)
+    for (int r = 0; r < nleft; ++r) Wl[r * KMAX + tid] = Wl[r * KMAX + tid] / wn_s[tid];
 #pragma unroll
   for (int j = 0; j < KT; ++j)
 #pragma unroll
@@ -796,8 +809,10 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
   for (;;) {
     double cacc = 0.0;
     const bool want_cost = sc.cost_check && it >= 1;
-    for (int tgp = 0; tgp < (tile_valid ? ngroups : 0); ++tgp) {   // a warp without a tile only takes part in the reductions
+    // a warp without a tile only takes part in the reductions (and in the leftover rows on the last rank)
+    for (int tgp = 0; tgp < ((tile_valid || has_left) ? ngroups : 0); ++tgp) {
       const int n0 = tgp * 16;
+      if (tile_valid) {
       double vcur[4];
       if (!VSMEM) load_v4(tgp, vcur);                                // in flight during GEMM 1 (and the other CTA's work)
       // GEMM 1: lambda tile = W * H for 16 history columns (even columns -> c0, odd -> c1)
@@ -847,68 +862,63 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
             dmma884(gacc[j][0], gacc[j][1], rt[3], a23.y);
           }
         }
-    }
-    WS_TICK(3);
-    if (left_warp) {
-      // leftover rows: lambda / ratio with lanes <-> history columns (4 per lane), then G with lanes <-> atoms
-      for (int r = 0; r < nleft; ++r) {
-        const double* wr = Wl + r * KMAX;
-        double a[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k < Ru; ++k) {
-          const double wv = wr[k];
-          const double* hk = Hs + (size_t)k * HSd + lane;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (32 * q < NP) a[q] = fma(wv, hk[32 * q], a[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int t = lane + 32 * q;
-          if (t < NP) {
+      }
+      // leftover rows for the 16 history columns of this group, on the warp that owns the group
+      if (has_left && (WARPS - 1 - tgp % WARPS) == warp) {
+        const int o = tgp % WARPS;
+        double* rlw = rlp + (size_t)o * nleft * 16;
+        double* glw = Glp + (size_t)o * nleft * KMAX;
+        const int t16 = lane & 15, kh = lane >> 4;
+        const double* hcol = Hs + n0 + t16;
+        for (int r = 0; r < nleft; ++r) {             // lambda and ratio: (column, half of the atoms) per lane
+          const double* wr = Wl + r * KMAX;
+          double a0 = 0.0, a1 = 0.0;
+          int k = kh;
+          for (; k + 2 < Ru; k += 4) {
+            a0 = fma(wr[k], hcol[(size_t)k * HSd], a0);
+            a1 = fma(wr[k + 2], hcol[(size_t)(k + 2) * HSd], a1);
+          }
+          if (k < Ru) a0 = fma(wr[k], hcol[(size_t)k * HSd], a0);
+          double a = a0 + a1;
+          a += __shfl_xor_sync(0xffffffffu, a, 16);
+          if (kh == 0) {
+            const int t = n0 + t16;
             double rr = 0.0;
             if (t < n) {
-              const double lam = fmax(a[q], flr);
+              const double lam = fmax(a, flr);
               const double v = fmax(Vs[(size_t)t * VS + TPC * 8 + r], flr);
               rr = v * fast_rcp(lam);
               if (want_cost) cacc += fma(v, fast_log(rr, tab), lam - v);
             }
-            rl[r * NP + t] = rr;
+            rlw[r * 16 + t16] = rr;
           }
         }
-      }
-      __syncwarp();
-      for (int r = 0; r < nleft; ++r)
-        for (int k = lane; k < KMAX; k += 32) {
-          double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-          if (k < Ru) {
-            const double* hk = Hs + (size_t)k * HSd;
-            const double* rr = rl + r * NP;
-            for (int t = 0; t < NP; t += 4) {       // H is zero-padded up to NP, rl is zero beyond n
-              const double2 h01 = *reinterpret_cast<const double2*>(hk + t), h23 = *reinterpret_cast<const double2*>(hk + t + 2);
-              const double2 r01 = *reinterpret_cast<const double2*>(rr + t), r23 = *reinterpret_cast<const double2*>(rr + t + 2);
-              g0 = fma(r01.x, h01.x, g0);
-              g1 = fma(r01.y, h01.y, g1);
-              g2 = fma(r23.x, h23.x, g2);
-              g3 = fma(r23.y, h23.y, g3);
+        __syncwarp();
+        for (int k = lane; k < KMAX; k += 32) {       // this group's part of G: atom per lane (H is zero beyond Ru)
+          const double* hk = Hs + (size_t)k * HSd + n0;
+          for (int r = 0; r < nleft; ++r) {
+            const double* rr = rlw + r * 16;
+            double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) {
+              g0 = fma(rr[q], hk[q], g0);
+              g1 = fma(rr[q + 1], hk[q + 1], g1);
             }
+            const double gp = g0 + g1;
+            glw[r * KMAX + k] = (tgp < WARPS) ? gp : glw[r * KMAX + k] + gp;
           }
-          Gl[r * KMAX + k] = (g0 + g1) + (g2 + g3);
         }
-      __syncwarp();
+        __syncwarp();
+      }
     }
     WS_TICK(3);
     // column reductions: cw_k = sum_f w, s_k = sum_f G.*w                               :215-221
-    if (left_warp) {
-      left_partial(0, [&](int r, int k) { return Wl[r * KMAX + k]; });
-      left_partial(1, [&](int r, int k) { return Gl[r * KMAX + k] * Wl[r * KMAX + k]; });
-    } else {
-      warp_partial(0, [&](int j, int e) { return w[j][e]; });
-      warp_partial(1, [&](int j, int e) { return gacc[j][e] * w[j][e]; });
-    }
+    warp_partial(0, [&](int j, int e) { return w[j][e]; });
+    warp_partial(1, [&](int j, int e) { return gacc[j][e] * w[j][e]; });
     cacc = warp_sum(cacc);
     if (lane == 0) scratch[warp] = cacc;
     double div = 0.0;
-    cluster_combine(2, true, &div);
+    cluster_combine(2, true, &div, LEFT_SUMS);
     WS_TICK(4);
 #ifdef SNMFNAT_WS_PROBE
     if (probe) atomicAdd(&g_ws_probe[8], 1ull);
@@ -937,28 +947,20 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         w[j][e] = (k < Ru) ? wv * dmw * fast_rcp(dpw) : 0.0;
         gacc[j][e] = 0.0;
       }
-    // column normalisation                                                              :242
-    if (left_warp) {
-      for (int i = lane; i < nleft * KMAX; i += 32) {
-        const int k = i % KMAX;
-        const double wv = Wl[i], hs = hs_s[k];
+    if (has_left && tid < KMAX) {                  // thread k owns atom k of the leftover rows
+      const int k = tid;
+      const double hs = hs_s[k];
+      for (int r = 0; r < nleft; ++r) {
+        const double wv = Wl[r * KMAX + k];
         const double dpw = fmax(hs + tot[KMAX + k] * wv, flr);
-        const double dmw = Gl[i] + (hs * tot[k]) * wv;
-        Wl[i] = (k < Ru) ? wv * dmw * fast_rcp(dpw) : 0.0;
+        const double dmw = Gl[r * KMAX + k] + (hs * tot[k]) * wv;
+        Wl[r * KMAX + k] = (k < Ru) ? wv * dmw * fast_rcp(dpw) : 0.0;
       }
-      __syncwarp();
     }
     WS_TICK(5);
-    if (left_warp) left_partial(0, [&](int r, int k) { return Wl[r * KMAX + k] * Wl[r * KMAX + k]; });
-    else warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
-    cluster_combine(1, false, nullptr, true);
-    if (left_warp) {
-      for (int i = lane; i < nleft * KMAX; i += 32) {
-        const int k = i % KMAX;
-        if (k < Ru) Wl[i] = Wl[i] * tot[k];
-      }
-      __syncwarp();   // the next pass reads every atom of the row from every lane
-    }
+    // column normalisation                                                              :242
+    warp_partial(0, [&](int j, int e) { return w[j][e] * w[j][e]; });
+    cluster_combine(1, false, nullptr, LEFT_SQ, true);
 #pragma unroll
     for (int j = 0; j < KT; ++j)
 #pragma unroll
@@ -980,8 +982,8 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       const int k = 8 * j + 2 * tg + e;
       if (row_valid && k < Ru) Bnext[(size_t)(n_rem + k) * LDF + frow] = w[j][e];
     }
-  if (left_warp)
-    for (int i = lane; i < nleft * KMAX; i += 32) {
+  if (has_left)
+    for (int i = tid; i < nleft * KMAX; i += THREADS) {
       const int r = i / KMAX, k = i - r * KMAX;
       if (k < Ru) Bnext[(size_t)(n_rem + k) * LDF + NFT * 8 + r] = Wl[i];
     }
@@ -1018,18 +1020,19 @@ static bool wsolve_geom_ok(const OnlineDims& d, int CL, int TPC) {
 bool wsolve_fast_supported(snmfnat_ctx* ctx, const OnlineDims& d) {
   if (d.R_a > 64 || d.R_a < 1) return false;
   if (!wsolve_geom_ok(d, 4, 16)) return false;   // both geometries cover 64 full tiles + 1 leftover
-  const size_t bytes = d.R_a <= 56 ? WfLayout<7, 4, 16, true>(d.m_a).bytes : WfLayout<8, 4, 16, true>(d.m_a).bytes;
+  const size_t bytes = d.R_a <= 56 ? WfLayout<7, 4, 16, true>(d.m_a, d.F % 8).bytes : WfLayout<8, 4, 16, true>(d.m_a, d.F % 8).bytes;
   return (int)bytes <= ctx->max_smem_optin;
 }
 
 template <int KT, int CL, int TPC, bool VSMEM>
 static void launch_wsolve_variant(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
                                   const TraceArrays& t, int has_trace, int n_active, int g_step, const double2* tab) {
-  const size_t smem = WfLayout<KT, CL, TPC, VSMEM>(d.m_a).bytes;
+  const size_t smem = WfLayout<KT, CL, TPC, VSMEM>(d.m_a, d.F % 8).bytes;
   auto kern = wsolve_fast_kernel<KT, CL, TPC, VSMEM>;
   SN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (!VSMEM) SN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  kern<<<dim3(CL * n_active), dim3((TPC + 1) * 32), smem, ctx->stream>>>(d, sc, st, t, has_trace, g_step, tab);
+  kern<<<dim3(CL * n_active), dim3(WfLayout<KT, CL, TPC, VSMEM>::WARPS * 32), smem, ctx->stream>>>(d, sc, st, t, has_trace,
+                                                                                                 g_step, tab);
 }
 
 void launch_wsolve_fast(snmfnat_ctx* ctx, const OnlineDims& d, const OnlineScalars& sc, const SlotState& st,
