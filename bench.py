@@ -453,9 +453,10 @@ def run_ours(args, rank, world, local_rank):
                          "hsolve": "multi-stream kernel (DESIGN.md 4.1): 3/4 of the flops as FP64 tensor-core tiles from registers, 1/4 "
                                    "as shared-memory mat-vecs; the per-iteration exchange over distributed shared memory is 30 % of "
                                    "an iteration (profiles/r02_hsolve_ms_probe.txt)",
-                         "wsolve": "the GEMM loop runs at 85-93 % of the FP64 pipe (profiles/r02_wsolve_probe.txt); the fraction "
-                                   "reported here divides ALGORITHMIC flops by the whole kernel time: padding 1.33x, rcp/log of the "
-                                   "ratio step 1.2x, one cost-only pass per solve, two exchanges per pass (DESIGN.md 4.2)"}.get(dom),
+                         "wsolve": "16 warps per CTA at 128 registers; the tile loop runs at 80-86 % of the FP64 pipe "
+                                   "(profiles/r02_wsolve_probe.txt); the fraction reported here divides ALGORITHMIC flops by the "
+                                   "whole kernel time: padding 1.31x, rcp/log of the ratio step 1.2x, one cost-only pass per "
+                                   "solve, two exchanges per pass (DESIGN.md 4.2)"}.get(dom),
                      "note": "fp64 = FP64 FMA pipe (DFMA issue rate); tensor = FP64 tensor-core mma.sync m8n8k4 "
                              "(MEASURED_PEAKS.json holds no FP64 figure, so the FP64 peaks are measured by "
                              "tools/peaks_fp64); achieved = SURVEY.md 8(d) algorithmic flops / CUDA-event time"})
