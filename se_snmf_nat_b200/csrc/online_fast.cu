@@ -682,14 +682,26 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
 
   // per-warp partial of a per-column quantity -> red[which][warp][k]
   auto warp_partial = [&](int which, auto&& f) {
+    // Sums over the 8 fragment rows (the lanes that share tg) of 2 KT per-lane values.  Instead of three shuffles per
+    // value, eight values are reduced together: at every level a lane keeps the half of the values its own row bit selects
+    // and hands the other half to its partner, so 4 + 2 + 1 exchanges finish eight sums, each ending up on one of the
+    // eight lanes (same pairing order (g^1, g^2, g^4) as a per-value butterfly: bit-identical sums).
     double* rw = red + ((size_t)which * WARPS + warp) * KMAX;
+    const bool b0 = g & 1, b1 = g & 2, b2 = g & 4;
 #pragma unroll
-    for (int j = 0; j < KT; ++j)
+    for (int base = 0; base < 2 * KT; base += 8) {
+      double x[8];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const double s = rows8_sum_f(f(j, e));
-        if (g == 0) rw[8 * j + 2 * tg + e] = s;
-      }
+      for (int i = 0; i < 8; ++i) x[i] = (base + i < 2 * KT) ? f((base + i) >> 1, (base + i) & 1) : 0.0;
+      double y[4], z[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = (b0 ? x[i + 4] : x[i]) + __shfl_xor_sync(0xffffffffu, b0 ? x[i] : x[i + 4], 4);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) z[i] = (b1 ? y[i + 2] : y[i]) + __shfl_xor_sync(0xffffffffu, b1 ? y[i] : y[i + 2], 8);
+      const double s = (b2 ? z[1] : z[0]) + __shfl_xor_sync(0xffffffffu, b2 ? z[0] : z[1], 16);
+      const int v = base + (b0 ? 4 : 0) + (b1 ? 2 : 0) + (b2 ? 1 : 0);     // the value whose sum this lane holds
+      if (v < 2 * KT) rw[8 * (v >> 1) + 2 * tg + (v & 1)] = s;
+    }
   };
   // what the leftover rows add to the CTA partial of column k (last rank only; evaluated inside cluster_combine by the
   // thread that sums column k): squares for the norms, or cw_k = sum w / s_k = sum G.*w, with G gathered from the owner
