@@ -18,6 +18,7 @@
 //   neutral by construction (V pad = floor, W pad = 0, H pad = 0) so the inner loops carry no predicates.
 //   v./lambda uses a Newton reciprocal and the KL cost a table-driven log (|err| < 4e-16 absolute).
 #include <cooperative_groups.h>
+#include <type_traits>
 #include <cmath>
 #include "online.cuh"
 #include "online_dev.cuh"
@@ -818,9 +819,13 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       dst[q] = x;
     }
   };
-  for (;;) {
-    double cacc = 0.0;
-    const bool want_cost = sc.cost_check && it >= 1;
+  double cacc = 0.0;
+  bool want_cost = false;
+  // One pass over the history columns, compiled once per number of atom tiles in use (kt = ceil(Ru / 8)): with the tile
+  // count a compile-time constant the loop body is straight-line code and the fragment loads can move ahead of the mma.
+  auto tile_pass = [&](auto ktc) {
+    constexpr int KTC = decltype(ktc)::value;
+
     // a warp without a tile only takes part in the reductions (and in the leftover rows on the last rank)
     for (int tgp = 0; tgp < ((tile_valid || has_left) ? ngroups : 0); ++tgp) {
       const int n0 = tgp * 16;
@@ -830,8 +835,7 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       // GEMM 1: lambda tile = W * H for 16 history columns (even columns -> c0, odd -> c1)
       double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
 #pragma unroll
-      for (int j = 0; j < KT; ++j)
-        if (j < kt) {
+      for (int j = 0; j < KTC; ++j) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const double2 b = *reinterpret_cast<const double2*>(Hs + (size_t)(8 * j + 2 * tg + e) * HSd + n0 + 2 * g);
@@ -851,22 +855,21 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
       }
       // GEMM 2: G tile += (v./lambda) * H'
 #pragma unroll
-      for (int j = 0; j < KT; j += 2)
-        if (j < kt) {
+      for (int j = 0; j < KTC; j += 2) {
           const double* hp = Hs + (size_t)(8 * j + g) * HSd + n0 + 4 * tg;
           const double2 a01 = *reinterpret_cast<const double2*>(hp);
           const double2 a23 = *reinterpret_cast<const double2*>(hp + 2);
-          if (j + 1 < KT && j + 1 < kt) {
+          if (j + 1 < KTC) {
             const double2 b01 = *reinterpret_cast<const double2*>(hp + 8 * HSd);
             const double2 b23 = *reinterpret_cast<const double2*>(hp + 8 * HSd + 2);
             dmma884(gacc[j][0], gacc[j][1], rt[0], a01.x);
-            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[0], b01.x);
+            dmma884(gacc[j + 1 < KTC ? j + 1 : j][0], gacc[j + 1 < KTC ? j + 1 : j][1], rt[0], b01.x);
             dmma884(gacc[j][0], gacc[j][1], rt[1], a01.y);
-            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[1], b01.y);
+            dmma884(gacc[j + 1 < KTC ? j + 1 : j][0], gacc[j + 1 < KTC ? j + 1 : j][1], rt[1], b01.y);
             dmma884(gacc[j][0], gacc[j][1], rt[2], a23.x);
-            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[2], b23.x);
+            dmma884(gacc[j + 1 < KTC ? j + 1 : j][0], gacc[j + 1 < KTC ? j + 1 : j][1], rt[2], b23.x);
             dmma884(gacc[j][0], gacc[j][1], rt[3], a23.y);
-            dmma884(gacc[j + 1 < KT ? j + 1 : j][0], gacc[j + 1 < KT ? j + 1 : j][1], rt[3], b23.y);
+            dmma884(gacc[j + 1 < KTC ? j + 1 : j][0], gacc[j + 1 < KTC ? j + 1 : j][1], rt[3], b23.y);
           } else {
             dmma884(gacc[j][0], gacc[j][1], rt[0], a01.x);
             dmma884(gacc[j][0], gacc[j][1], rt[1], a01.y);
@@ -923,6 +926,16 @@ wsolve_fast_kernel(OnlineDims d, OnlineScalars sc, SlotState st, TraceArrays tr,
         __syncwarp();
       }
     }
+  };
+  auto dispatch = [&](auto self, auto c) -> void {
+    constexpr int C = decltype(c)::value;
+    if (kt == C) tile_pass(c);
+    else if constexpr (C > 0) self(self, std::integral_constant<int, C - 1>{});
+  };
+  for (;;) {
+    cacc = 0.0;
+    want_cost = sc.cost_check && it >= 1;
+    dispatch(dispatch, std::integral_constant<int, KT>{});
     WS_TICK(3);
     // column reductions: cw_k = sum_f w, s_k = sum_f G.*w                               :215-221
     warp_partial(0, [&](int j, int e) { return w[j][e]; });
