@@ -16,6 +16,7 @@ for ln in out.splitlines():
     m = re.search(r"Function : (\S+)", ln)
     if m:
         cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        cur = cur.replace("(anonymous namespace)::", "")
         cur = re.sub(r"\(.*", "", cur)[:70]
         cnt[cur] = collections.Counter()
         continue
