@@ -182,3 +182,35 @@ def test_snmf_mdi_keeps_observed_part():
 
 def O_rel(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(a)
+
+
+def test_semi_supervised_switches_follow_the_reference_branch_order(bases, wavs, rng_inputs):
+    """bnmf_sep_event_RT_IS16.m:125-139 is an if / elseif chain: with basis_update_N set, basis_update_E is never looked at
+    (the `N && E` branch is unreachable); either switch changes the activations of the hop, the dictionaries of g do not
+    move (the W of the solve is discarded, :150-154), and the joint solve still lowers the KL cost monotonically."""
+    h_init, Ad = rng_inputs
+    Bx, Bd = bases["B_DFT_x"], bases["B_DFT_d"]
+    pcm = wavs["M03_in"][8000:8000 + 160 * 22].astype(float)
+    outs = {}
+    for name, over in (("sup", {}), ("N", dict(basis_update_N=1)), ("E", dict(basis_update_E=1)),
+                       ("NE", dict(basis_update_N=1, basis_update_E=1))):
+        p = dict(O.default_params(), adapt_train_N=0, **over)
+        g = O.init_buff(Bx, Bd, Bx, Bd, p, Ad_blk_init=Ad)
+        y = np.zeros(640)
+        xs = []
+        for l in range(1, 23):   # past the init_N_len = 15 noise-only frames
+            y = np.concatenate([y[160:], pcm[(l - 1) * 160:l * 160]])
+            _, _, xt, g = O.bnmf_sep_event_RT_IS16(y, l, g, p, h_init=h_init)
+            xs.append(xt.copy())
+        outs[name] = np.concatenate(xs)
+        assert np.array_equal(g.B_DFT_d, Bd) and np.array_equal(g.B_DFT_x, Bx)
+    assert np.array_equal(outs["NE"], outs["N"])
+    assert not np.array_equal(outs["N"], outs["sup"]) and not np.array_equal(outs["E"], outs["sup"])
+    assert not np.array_equal(outs["N"], outs["E"])
+    # the joint W/H iteration on one frame: KL + sparsity cost is non-increasing (multiplicative updates)
+    v = np.abs(np.random.RandomState(3).randn(513, 1)) ** 2 * 1e6 + 1e-9
+    W = np.concatenate([Bx, Bd], axis=1)
+    wi = np.concatenate([np.zeros(100, bool), np.ones(100, bool)])
+    _, _, obj = O.sparse_nmf(v, init_w=W, init_h=h_init, max_iter=40, conv_eps=0.0, sparsity=5.0, w_update_ind=wi,
+                             h_update_ind=np.ones(200, bool))
+    assert np.all(np.diff(obj["cost"]) <= 1e-9 * obj["cost"][:-1])
